@@ -1,0 +1,366 @@
+// Training-mode BatchNorm pieces on NHWC bf16 activations (fp32 statistics), sm_100a.
+// Replaces norm_layer(...) of ConvBnRelu (/root/reference/furnace/seg_opr/seg_oprs.py:34,42), the
+// BasicBlock bn1/bn2 + residual add + ReLU (/root/reference/furnace/base_model/resnet.py:33-53) and the
+// statistics half of apex SyncBatchNorm (train.py:54-55).  All HBM-bound: 16-byte vector accesses,
+// per-channel reductions through shared memory + one fp32 atomic per (CTA, channel).
+#include "nhwc_vec.cuh"
+
+namespace {
+constexpr int kThreads = 256;
+
+// Generic per-channel column reduction over [npix, C] with NACC accumulators per channel.
+// Functor: f(pix, c8, float acc[NACC][8]) accumulates one 8-channel vector of one pixel.
+template <int NACC, typename F>
+__device__ __forceinline__ void column_reduce(long long npix, int C8, float* const (&outs)[NACC], F f) {
+    extern __shared__ float s_buf[];  // [lanes][groups][NACC][8]
+    const int groups = min(C8, kThreads);
+    const int lanes = kThreads / groups;
+    const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+    const long long chunk = (npix + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * chunk;
+    const long long p1 = (p0 + chunk < npix) ? p0 + chunk : npix;
+    for (int g0 = 0; g0 < C8; g0 += groups) {
+        const int cg = g0 + g;
+        float acc[NACC][8];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[a][k] = 0.f;
+        if (cg < C8 && lane < lanes)
+            for (long long pp = p0 + lane; pp < p1; pp += lanes) f(pp, cg, acc);
+        if (lane < lanes) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s_buf[((lane * groups + g) * NACC + a) * 8 + k] = acc[a][k];
+        }
+        __syncthreads();
+        // thread (lane, g) finishes accumulator slots striped over lanes
+        if (cg < C8 && lane < lanes) {
+            for (int slot = lane; slot < NACC * 8; slot += lanes) {
+                float s = 0.f;
+                for (int l = 0; l < lanes; ++l) s += s_buf[(l * groups + g) * NACC * 8 + slot];
+                atomicAdd(outs[slot / 8] + cg * 8 + (slot % 8), s);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, int cs, long long npix, int C8, float* sum, float* sumsq) {
+    float* const outs[2] = {sum, sumsq};
+    column_reduce<2>(npix, C8, outs, [&](long long p, int cg, float (&acc)[2][8]) {
+        float v[8];
+        Vec8<__nv_bfloat16>::load(x + p * cs + cg * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[0][k] += v[k]; acc[1][k] += v[k] * v[k]; }
+    });
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* mean, float* invstd, float* scale, float* shift,
+                                   float* running_mean, float* running_var) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m = (double)sum[c] / count;
+    double var = (double)sumsq[c] / count - m * m;  // biased (normalisation)
+    if (var < 0.0) var = 0.0;
+    float is = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    if (mean) mean[c] = (float)m;
+    if (invstd) invstd[c] = is;
+    if (scale) scale[c] = g * is;
+    if (shift) shift[c] = b - (float)m * g * is;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    if (running_var) {
+        double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+template <bool kRelu, bool kRes>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ scale,
+                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int rcs,
+                __nv_bfloat16* __restrict__ y, int ycs, long long npix, int C8) {
+    const long long total = npix * C8;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        int c8 = (int)(i % C8);
+        long long p = i / C8;
+        float v[8], sc[8], sh[8];
+        Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, v);
+        ldg8f(scale + c8 * 8, sc);
+        ldg8f(shift + c8 * 8, sh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+        if (kRes) {
+            float r[8];
+            Vec8<__nv_bfloat16>::load(res + p * rcs + c8 * 8, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += r[k];
+        }
+        if (kRelu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        }
+        Vec8<__nv_bfloat16>::store(y + p * ycs + c8 * 8, v);
+    }
+}
+
+template <bool kRelu>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ y, int ycs,
+                     const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, long long npix, int C8, float* sum_dz, float* sum_dz_xhat) {
+    float* const outs[2] = {sum_dz, sum_dz_xhat};
+    column_reduce<2>(npix, C8, outs, [&](long long p, int cg, float (&acc)[2][8]) {
+        float g[8], xv[8], m[8], is[8];
+        Vec8<__nv_bfloat16>::load(dy + p * dycs + cg * 8, g);
+        Vec8<__nv_bfloat16>::load(x + p * xcs + cg * 8, xv);
+        ldg8f(mean + cg * 8, m);
+        ldg8f(invstd + cg * 8, is);
+        if (kRelu) {
+            float yv[8];
+            Vec8<__nv_bfloat16>::load(y + p * ycs + cg * 8, yv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[0][k] += g[k]; acc[1][k] += g[k] * (xv[k] - m[k]) * is[k]; }
+    });
+}
+
+template <bool kRelu, bool kDres>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ y, int ycs,
+                    const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat, float inv_count,
+                    __nv_bfloat16* __restrict__ dx, int dxcs, __nv_bfloat16* __restrict__ dres, int drcs,
+                    long long npix, int C8) {
+    const long long total = npix * C8;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        int c8 = (int)(i % C8);
+        long long p = i / C8;
+        float g[8], xv[8], m[8], is[8], ga[8], s1[8], s2[8], o[8];
+        Vec8<__nv_bfloat16>::load(dy + p * dycs + c8 * 8, g);
+        Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, xv);
+        ldg8f(mean + c8 * 8, m);
+        ldg8f(invstd + c8 * 8, is);
+        ldg8f(gamma + c8 * 8, ga);
+        ldg8f(sum_dz + c8 * 8, s1);
+        ldg8f(sum_dz_xhat + c8 * 8, s2);
+        if (kRelu) {
+            float yv[8];
+            Vec8<__nv_bfloat16>::load(y + p * ycs + c8 * 8, yv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float xhat = (xv[k] - m[k]) * is[k];
+            o[k] = ga[k] * is[k] * (g[k] - s1[k] * inv_count - xhat * s2[k] * inv_count);
+        }
+        Vec8<__nv_bfloat16>::store(dx + p * dxcs + c8 * 8, o);
+        if (kDres) Vec8<__nv_bfloat16>::store(dres + p * drcs + c8 * 8, g);
+    }
+}
+
+// ---------------------------------------------------------------- channel attention scale (ARM / FFM)
+template <bool kAdd>
+__global__ void __launch_bounds__(kThreads)
+chan_scale_fwd_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ a, float base,
+                      const __nv_bfloat16* __restrict__ add, int acs, __nv_bfloat16* __restrict__ y, int ycs, int HW,
+                      int C8, long long total) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        int c8 = (int)(i % C8);
+        long long p = i / C8;
+        int n = (int)(p / HW);
+        float v[8], av[8];
+        Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, v);
+        ldg8f(a + (long long)n * C8 * 8 + c8 * 8, av);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= base + 1.f / (1.f + __expf(-av[k]));
+        if (kAdd) {
+            float r[8];
+            Vec8<__nv_bfloat16>::load(add + p * acs + c8 * 8, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += r[k];
+        }
+        Vec8<__nv_bfloat16>::store(y + p * ycs + c8 * 8, v);
+    }
+}
+
+// grid = (chunks, N): per image column reduction for da plus elementwise dx
+__global__ void __launch_bounds__(kThreads)
+chan_scale_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ x, int xcs,
+                      const float* __restrict__ a, float base, __nv_bfloat16* __restrict__ dx, int dxcs, float* da,
+                      int HW, int C8) {
+    extern __shared__ float s_buf[];
+    const int n = blockIdx.y;
+    const int groups = min(C8, kThreads);
+    const int lanes = kThreads / groups;
+    const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+    const int chunk = (HW + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+    for (int g0 = 0; g0 < C8; g0 += groups) {
+        const int cg = g0 + g;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        if (cg < C8 && lane < lanes) {
+            float av[8], sg[8];
+            ldg8f(a + (long long)n * C8 * 8 + cg * 8, av);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sg[k] = 1.f / (1.f + __expf(-av[k]));
+            for (int pp = p0 + lane; pp < p1; pp += lanes) {
+                long long p = (long long)n * HW + pp;
+                float gv[8], xv[8], o[8];
+                Vec8<__nv_bfloat16>::load(dy + p * dycs + cg * 8, gv);
+                Vec8<__nv_bfloat16>::load(x + p * xcs + cg * 8, xv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    o[k] = gv[k] * (base + sg[k]);
+                    acc[k] += gv[k] * xv[k];
+                }
+                Vec8<__nv_bfloat16>::store(dx + p * dxcs + cg * 8, o);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] *= sg[k] * (1.f - sg[k]);
+        }
+        if (lane < lanes) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_buf[(lane * groups + g) * 8 + k] = acc[k];
+        }
+        __syncthreads();
+        if (cg < C8 && lane < lanes) {
+            for (int slot = lane; slot < 8; slot += lanes) {
+                float s = 0.f;
+                for (int l = 0; l < lanes; ++l) s += s_buf[(l * groups + g) * 8 + slot];
+                atomicAdd(da + (long long)n * C8 * 8 + cg * 8 + slot, s);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static inline size_t colred_smem(int C8, int nacc) {
+    int groups = C8 < kThreads ? C8 : kThreads;
+    int lanes = kThreads / groups;
+    return sizeof(float) * (size_t)lanes * groups * nacc * 8;
+}
+static inline int colred_grid(long long npix, int C8) {
+    int groups = C8 < kThreads ? C8 : kThreads;
+    int lanes = kThreads / groups;
+    long long per_block = (long long)lanes * 16;  // >= 16 pixels per lane
+    long long need = (npix + per_block - 1) / per_block;
+    long long cap = (long long)tsb_num_sms() * 8;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+}  // namespace
+
+#define TSB_VEC_OK(C, cs, ptr) ((C) % 8 == 0 && (cs) % 8 == 0 && tsb_aligned16(ptr))
+
+extern "C" int tsb_bn_stats(const void* x, int cs, long long npix, int C, float* sum, float* sumsq, tsb_stream_t stream) {
+    TSB_REQUIRE(x && sum && sumsq && npix > 0, "tsb_bn_stats: bad args");
+    TSB_REQUIRE(TSB_VEC_OK(C, cs, x), "tsb_bn_stats: C and cs must be multiples of 8");
+    int C8 = C / 8;
+    bn_stats_kernel<<<colred_grid(npix, C8), kThreads, colred_smem(C8, 2), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, cs, npix, C8, sum, sumsq);
+    TSB_CUDA_CHECK_LAUNCH("bn_stats");
+    return TSB_OK;
+}
+
+extern "C" int tsb_bn_finalize(const float* sum, const float* sumsq, double count, int C, const float* gamma,
+                               const float* beta, float eps, float momentum, float* mean, float* invstd, float* scale,
+                               float* shift, float* running_mean, float* running_var, tsb_stream_t stream) {
+    TSB_REQUIRE(sum && sumsq && count > 0 && C > 0, "tsb_bn_finalize: bad args");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, count, C, gamma, beta, eps, momentum, mean, invstd, scale, shift, running_mean, running_var);
+    TSB_CUDA_CHECK_LAUNCH("bn_finalize");
+    return TSB_OK;
+}
+
+extern "C" int tsb_bn_apply(const void* x, int xcs, const float* scale, const float* shift, const void* residual,
+                            int rcs, int relu, void* y, int ycs, long long npix, int C, tsb_stream_t stream) {
+    TSB_REQUIRE(x && scale && shift && y && npix > 0, "tsb_bn_apply: bad args");
+    TSB_REQUIRE(TSB_VEC_OK(C, xcs, x) && TSB_VEC_OK(C, ycs, y) && (!residual || TSB_VEC_OK(C, rcs, residual)),
+                "tsb_bn_apply: C and channel strides must be multiples of 8");
+    int C8 = C / 8;
+    int grid = tsb_grid_for(npix * C8, kThreads, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define L(R, S) bn_apply_kernel<R, S><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)x, xcs, scale, shift, (const __nv_bfloat16*)residual, rcs, (__nv_bfloat16*)y, ycs, npix, C8)
+    if (relu) { if (residual) L(true, true); else L(true, false); }
+    else { if (residual) L(false, true); else L(false, false); }
+#undef L
+    TSB_CUDA_CHECK_LAUNCH("bn_apply");
+    return TSB_OK;
+}
+
+extern "C" int tsb_bn_bwd_reduce(const void* dy, int dycs, const void* y, int ycs, const void* x, int xcs,
+                                 const float* mean, const float* invstd, int relu, long long npix, int C, float* sum_dz,
+                                 float* sum_dz_xhat, tsb_stream_t stream) {
+    TSB_REQUIRE(dy && x && mean && invstd && sum_dz && sum_dz_xhat && npix > 0 && (!relu || y), "tsb_bn_bwd_reduce: bad args");
+    TSB_REQUIRE(TSB_VEC_OK(C, dycs, dy) && TSB_VEC_OK(C, xcs, x) && (!relu || TSB_VEC_OK(C, ycs, y)), "tsb_bn_bwd_reduce: alignment");
+    int C8 = C / 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (relu)
+        bn_bwd_reduce_kernel<true><<<colred_grid(npix, C8), kThreads, colred_smem(C8, 2), st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, npix, C8, sum_dz, sum_dz_xhat);
+    else
+        bn_bwd_reduce_kernel<false><<<colred_grid(npix, C8), kThreads, colred_smem(C8, 2), st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, npix, C8, sum_dz, sum_dz_xhat);
+    TSB_CUDA_CHECK_LAUNCH("bn_bwd_reduce");
+    return TSB_OK;
+}
+
+extern "C" int tsb_bn_bwd_apply(const void* dy, int dycs, const void* y, int ycs, const void* x, int xcs,
+                                const float* mean, const float* invstd, const float* gamma, const float* sum_dz,
+                                const float* sum_dz_xhat, double count, int relu, void* dx, int dxcs, void* dres,
+                                int drcs, long long npix, int C, tsb_stream_t stream) {
+    TSB_REQUIRE(dy && x && mean && invstd && gamma && sum_dz && sum_dz_xhat && dx && npix > 0 && count > 0 && (!relu || y),
+                "tsb_bn_bwd_apply: bad args");
+    TSB_REQUIRE(TSB_VEC_OK(C, dycs, dy) && TSB_VEC_OK(C, xcs, x) && TSB_VEC_OK(C, dxcs, dx) &&
+                (!relu || TSB_VEC_OK(C, ycs, y)) && (!dres || TSB_VEC_OK(C, drcs, dres)), "tsb_bn_bwd_apply: alignment");
+    int C8 = C / 8;
+    int grid = tsb_grid_for(npix * C8, kThreads, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    float inv_count = (float)(1.0 / count);
+#define L(R, D) bn_bwd_apply_kernel<R, D><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, gamma, sum_dz, sum_dz_xhat, inv_count, (__nv_bfloat16*)dx, dxcs, (__nv_bfloat16*)dres, drcs, npix, C8)
+    if (relu) { if (dres) L(true, true); else L(true, false); }
+    else { if (dres) L(false, true); else L(false, false); }
+#undef L
+    TSB_CUDA_CHECK_LAUNCH("bn_bwd_apply");
+    return TSB_OK;
+}
+
+extern "C" int tsb_chan_scale_fwd(const void* x, int xcs, const float* a, float base, const void* add, int acs, void* y,
+                                  int ycs, int N, int HW, int C, tsb_stream_t stream) {
+    TSB_REQUIRE(x && a && y && N > 0 && HW > 0, "tsb_chan_scale_fwd: bad args");
+    TSB_REQUIRE(TSB_VEC_OK(C, xcs, x) && TSB_VEC_OK(C, ycs, y) && (!add || TSB_VEC_OK(C, acs, add)) && tsb_aligned16(a), "tsb_chan_scale_fwd: alignment");
+    int C8 = C / 8;
+    long long total = (long long)N * HW * C8;
+    int grid = tsb_grid_for(total, kThreads, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (add)
+        chan_scale_fwd_kernel<true><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)x, xcs, a, base, (const __nv_bfloat16*)add, acs, (__nv_bfloat16*)y, ycs, HW, C8, total);
+    else
+        chan_scale_fwd_kernel<false><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)x, xcs, a, base, nullptr, 0, (__nv_bfloat16*)y, ycs, HW, C8, total);
+    TSB_CUDA_CHECK_LAUNCH("chan_scale_fwd");
+    return TSB_OK;
+}
+
+extern "C" int tsb_chan_scale_bwd(const void* dy, int dycs, const void* x, int xcs, const float* a, float base, void* dx,
+                                  int dxcs, float* da, int N, int HW, int C, tsb_stream_t stream) {
+    TSB_REQUIRE(dy && x && a && dx && da && N > 0 && HW > 0, "tsb_chan_scale_bwd: bad args");
+    TSB_REQUIRE(TSB_VEC_OK(C, dycs, dy) && TSB_VEC_OK(C, xcs, x) && TSB_VEC_OK(C, dxcs, dx) && tsb_aligned16(a), "tsb_chan_scale_bwd: alignment");
+    int C8 = C / 8;
+    int groups = C8 < kThreads ? C8 : kThreads;
+    int lanes = kThreads / groups;
+    int chunks = (HW + lanes * 16 - 1) / (lanes * 16);
+    int cap = (tsb_num_sms() * 8 + N - 1) / N;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    chan_scale_bwd_kernel<<<dim3(chunks, N), kThreads, colred_smem(C8, 1), (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)x, xcs, a, base, (__nv_bfloat16*)dx, dxcs, da, HW, C8);
+    TSB_CUDA_CHECK_LAUNCH("chan_scale_bwd");
+    return TSB_OK;
+}
