@@ -1,0 +1,174 @@
+"""ORACLE — test infrastructure only.
+
+Functional fp32 PyTorch restatement of the reference modules on the training-step hot path, driven by a
+state_dict that uses the REFERENCE's key names, so weights can be exchanged both ways.
+Each function cites the reference lines it restates. Pinned against the live reference modules by
+tests/test_oracle_vs_reference.py (authoring container) and tests/golden/*.
+
+Nothing under torchseg_b200/ imports this file.
+"""
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------------
+# ProbOhemCrossEntropy2d.forward — /root/reference/furnace/seg_opr/loss_opr.py:68-98
+# (with `1 - mask` → `~mask`, the torch>=1.2 shim of SURVEY.md App. C2)
+# --------------------------------------------------------------------------------------------------
+def ohem_ce(pred, target, ignore_label=255, thresh=0.7, min_kept=256, weight=None, return_aux=False):
+    b, c, h, w = pred.shape
+    target = target.reshape(-1)
+    valid_mask = target.ne(ignore_label)                                   # :70
+    target = target * valid_mask.long()                                    # :71
+    num_valid = int(valid_mask.sum())                                      # :72
+    prob = F.softmax(pred, dim=1)                                          # :75
+    prob = prob.transpose(0, 1).reshape(c, -1)                             # :76
+    threshold = thresh
+    if min_kept > num_valid:                                               # :78
+        pass
+    elif num_valid > 0:                                                    # :80
+        prob = prob.masked_fill(~valid_mask, 1)                            # :81
+        mask_prob = prob[target, torch.arange(len(target), dtype=torch.long, device=pred.device)]  # :82-83
+        if min_kept > 0:                                                   # :85
+            _, index = torch.sort(mask_prob)                               # :86
+            threshold_index = index[min(len(index), min_kept) - 1]         # :87
+            if mask_prob[threshold_index] > thresh:                        # :88
+                threshold = float(mask_prob[threshold_index])
+            kept_mask = mask_prob.le(threshold)                            # :90
+            target = target * kept_mask.long()
+            valid_mask = valid_mask * kept_mask
+    target = target.masked_fill(~valid_mask, ignore_label)                 # :95
+    target = target.view(b, h, w)
+    loss = F.cross_entropy(pred, target, weight=weight, ignore_index=ignore_label)  # :98
+    if return_aux:
+        return loss, valid_mask, threshold
+    return loss
+
+
+# SigmoidFocalLoss.forward — loss_opr.py:23-45
+def sigmoid_focal(pred, target, ignore_label, gamma=2.0, alpha=0.25):
+    b = target.shape[0]
+    pred = pred.reshape(b, -1, 1)
+    s = pred.sigmoid()
+    t = target.reshape(b, -1).float()
+    mask = t.ne(ignore_label).float()
+    t = mask * t
+    onehot = t.view(b, -1, 1)
+    max_val = (-s).clamp(min=0)
+    pos = (1 - s) ** gamma * (s - s * onehot)
+    neg = s ** gamma * (max_val + ((-max_val).exp() + (-s - max_val).exp()).log())
+    loss = -(alpha * pos + (1 - alpha) * neg).sum(dim=-1) * mask
+    return loss.mean()
+
+
+# --------------------------------------------------------------------------------------------------
+# building blocks
+# --------------------------------------------------------------------------------------------------
+def _bn(x, sd, prefix, eps, momentum, training, stats=None):
+    rm = sd.get(prefix + ".running_mean") if stats is None else stats.setdefault(prefix + ".running_mean", sd[prefix + ".running_mean"].clone())
+    rv = sd.get(prefix + ".running_var") if stats is None else stats.setdefault(prefix + ".running_var", sd[prefix + ".running_var"].clone())
+    if training and stats is None:
+        rm = rv = None  # pure batch statistics; running stats untouched
+    return F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training, momentum, eps)
+
+
+def conv_bn_relu(x, sd, prefix, stride, pad, dilation=1, has_bn=True, has_relu=True, eps=1e-5, momentum=0.1,
+                 training=True, stats=None):
+    """ConvBnRelu.forward — /root/reference/furnace/seg_opr/seg_oprs.py:39-46"""
+    x = F.conv2d(x, sd[prefix + ".conv.weight"], sd.get(prefix + ".conv.bias"), stride, pad, dilation)
+    if has_bn:
+        x = _bn(x, sd, prefix + ".bn", eps, momentum, training, stats)
+    if has_relu:
+        x = F.relu(x)
+    return x
+
+
+def basic_block(x, sd, prefix, stride, has_down, eps, momentum, training, stats=None):
+    """BasicBlock.forward — /root/reference/furnace/base_model/resnet.py:33-53"""
+    out = F.conv2d(x, sd[prefix + ".conv1.weight"], None, stride, 1)
+    out = F.relu(_bn(out, sd, prefix + ".bn1", eps, momentum, training, stats))
+    out = F.conv2d(out, sd[prefix + ".conv2.weight"], None, 1, 1)
+    out = _bn(out, sd, prefix + ".bn2", eps, momentum, training, stats)
+    residual = x
+    if has_down:
+        residual = F.conv2d(x, sd[prefix + ".downsample.0.weight"], None, stride, 0)
+        residual = _bn(residual, sd, prefix + ".downsample.1", eps, momentum, training, stats)
+    return F.relu(out + residual)
+
+
+def resnet18(x, sd, prefix, eps, momentum, training, stats=None):
+    """ResNet.forward (deep_stem=False, BasicBlock [2,2,2,2]) — resnet.py:126-184"""
+    x = F.conv2d(x, sd[prefix + ".conv1.weight"], None, 2, 3)
+    x = F.relu(_bn(x, sd, prefix + ".bn1", eps, momentum, training, stats))
+    x = F.max_pool2d(x, 3, 2, 1)
+    blocks = []
+    for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+        for bi in range(2):
+            st = stride if bi == 0 else 1
+            has_down = bi == 0 and li > 1
+            x = basic_block(x, sd, "%s.layer%d.%d" % (prefix, li, bi), st, has_down, eps, momentum, training, stats)
+        blocks.append(x)
+    return blocks
+
+
+def attention_refinement(x, sd, prefix, eps, momentum, training, stats=None):
+    """AttentionRefinement.forward — seg_oprs.py:207-212"""
+    fm = conv_bn_relu(x, sd, prefix + ".conv_3x3", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
+    se = F.adaptive_avg_pool2d(fm, 1)
+    se = conv_bn_relu(se, sd, prefix + ".channel_attention.1", 1, 0, has_relu=False, eps=eps, momentum=momentum,
+                      training=training, stats=stats)
+    return fm * torch.sigmoid(se)
+
+
+def feature_fusion(x1, x2, sd, prefix, eps, momentum, training, stats=None):
+    """FeatureFusion.forward — seg_oprs.py:233-238"""
+    fm = torch.cat([x1, x2], dim=1)
+    fm = conv_bn_relu(fm, sd, prefix + ".conv_1x1", 1, 0, eps=eps, momentum=momentum, training=training, stats=stats)
+    se = F.adaptive_avg_pool2d(fm, 1)
+    se = conv_bn_relu(se, sd, prefix + ".channel_attention.1", 1, 0, has_bn=False, has_relu=True)
+    se = conv_bn_relu(se, sd, prefix + ".channel_attention.2", 1, 0, has_bn=False, has_relu=False)
+    return fm + fm * torch.sigmoid(se)
+
+
+def bisenet_head_logits(x, sd, prefix, eps, momentum, training, stats=None):
+    """BiSeNetHead.forward up to the low-resolution logits — bisenet network.py:162-163"""
+    fm = conv_bn_relu(x, sd, prefix + ".conv_3x3", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
+    return F.conv2d(fm, sd[prefix + ".conv_1x1.weight"], sd[prefix + ".conv_1x1.bias"])
+
+
+def bisenet_r18_forward(data, sd, eps=1e-5, momentum=0.1, training=True, stats=None):
+    """BiSeNet.forward wiring — /root/reference/model/bisenet/cityscapes.bisenet.R18/network.py:75-111.
+    Returns the three LOW-resolution logit tensors (aux0 @1/16 scale 16, aux1 @1/8, main @1/8) and features."""
+    kw = dict(eps=eps, momentum=momentum, training=training, stats=stats)
+    sp = conv_bn_relu(data, sd, "spatial_path.conv_7x7", 2, 3, **kw)
+    sp = conv_bn_relu(sp, sd, "spatial_path.conv_3x3_1", 2, 1, **kw)
+    sp = conv_bn_relu(sp, sd, "spatial_path.conv_3x3_2", 2, 1, **kw)
+    sp = conv_bn_relu(sp, sd, "spatial_path.conv_1x1", 1, 0, **kw)
+    blocks = resnet18(data, sd, "context_path", eps, momentum, training, stats)
+    blocks = blocks[::-1]
+    gc = F.adaptive_avg_pool2d(blocks[0], 1)
+    gc = conv_bn_relu(gc, sd, "global_context.1", 1, 0, **kw)
+    gc = F.interpolate(gc, size=blocks[0].shape[2:], mode="bilinear", align_corners=True)
+    last = gc
+    pred_out = []
+    for i in range(2):
+        fm = attention_refinement(blocks[i], sd, "arms.%d" % i, eps, momentum, training, stats)
+        fm = fm + last
+        last = F.interpolate(fm, size=blocks[i + 1].shape[2:], mode="bilinear", align_corners=True)
+        last = conv_bn_relu(last, sd, "refines.%d" % i, 1, 1, **kw)
+        pred_out.append(last)
+    ffm = feature_fusion(sp, last, sd, "ffm", eps, momentum, training, stats)
+    pred_out.append(ffm)
+    lo = [bisenet_head_logits(pred_out[i], sd, "heads.%d" % i, eps, momentum, training, stats) for i in range(3)]
+    return lo, pred_out
+
+
+def bisenet_r18_loss(data, label, sd, min_kept, ignore_label=255, thresh=0.7, eps=1e-5, momentum=0.1, stats=None):
+    """training branch of BiSeNet.forward — network.py:103-109: main + aux0 + aux1, heads upsample x16/x8/x8"""
+    lo, _ = bisenet_r18_forward(data, sd, eps, momentum, True, stats)
+    scales = (16, 8, 8)
+    losses = []
+    for l, s in zip(lo, scales):
+        up = F.interpolate(l, scale_factor=s, mode="bilinear", align_corners=True)
+        losses.append(ohem_ce(up, label, ignore_label, thresh, min_kept))
+    return losses[2] + losses[0] + losses[1], lo

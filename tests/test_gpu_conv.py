@@ -1,0 +1,151 @@
+"""GPU parity tests of the tcgen05 implicit-GEMM convolution (fprop / dgrad / wgrad / stem) against
+F.conv2d autograd in fp32 on bf16-rounded operands. Tolerance 1e-2 of the output scale (bf16 path)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_err, bf16_round
+
+pytestmark = pytest.mark.gpu
+
+# (N, C, H, W, K, R, stride, pad, dil)
+CASES = [
+    (2, 64, 32, 32, 64, 3, 1, 1, 1),       # layer1-like
+    (2, 64, 32, 32, 128, 3, 2, 1, 1),      # layer2.0.conv1
+    (2, 128, 16, 16, 128, 3, 1, 1, 1),
+    (1, 256, 20, 28, 256, 3, 1, 2, 2),     # dilated, ragged spatial size (PSP layer3)
+    (2, 512, 8, 8, 128, 3, 1, 1, 1),       # ARM conv on a small map
+    (2, 64, 32, 32, 128, 1, 2, 0, 1),      # 1x1 stride-2 downsample
+    (2, 256, 16, 16, 256, 1, 1, 0, 1),     # FFM 1x1 (flat GEMM path)
+    (3, 64, 17, 23, 64, 3, 2, 1, 1),       # odd sizes, stride 2
+    (2, 128, 12, 12, 256, 3, 1, 4, 4),     # dilation 4
+    (4, 512, 1, 1, 128, 1, 1, 0, 1),       # global-context conv on a 1x1 map
+]
+
+
+def _ref(x, w, stride, pad, dil, gy):
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y = F.conv2d(xr, wr, None, stride, pad, dil)
+    y.backward(gy)
+    return y.detach(), xr.grad, wr.grad
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_fprop_dgrad_wgrad(cuda, case):
+    from torchseg_b200 import ops
+    N, C, H, W, K, R, stride, pad, dil = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = bf16_round(torch.randn(N, C, H, W, generator=g))
+    w = bf16_round(torch.randn(K, C, R, R, generator=g) / (C * R * R) ** 0.5)
+    P, Q = ops.conv_out_size(H, R, stride, pad, dil), ops.conv_out_size(W, R, stride, pad, dil)
+    gy = bf16_round(torch.randn(N, K, P, Q, generator=g))
+    y_ref, dx_ref, dw_ref = _ref(x, w, stride, pad, dil, gy)
+
+    xd = ops.to_nhwc(x.to(cuda))
+    wk = w.to(cuda).permute(0, 2, 3, 1).contiguous()              # KRSC fp32
+    wb = torch.empty((K, R, R, C), dtype=torch.bfloat16, device=cuda)
+    wt = torch.empty((C, R, R, K), dtype=torch.bfloat16, device=cuda)
+    ops.call("tsb_pack_weight", ops.ptr(wk), K, R, R, C, ops.ptr(wb), ops.ptr(wt), ops.stream())
+    stats = torch.zeros(2, K, device=cuda)
+    y = ops.conv_fprop(xd, wb, K, R, stride, pad, dil, stats=stats)
+    torch.cuda.synchronize()
+    e = rel_err(y, y_ref)
+    assert e < 1e-2, "fprop rel err %g" % e
+    yb = y.float()
+    assert rel_err(stats[0], yb.sum(dim=(0, 2, 3))) < 1e-3
+    assert rel_err(stats[1], (yb * yb).sum(dim=(0, 2, 3))) < 1e-3
+
+    gyd = ops.to_nhwc(gy.to(cuda))
+    dx = ops.conv_dgrad(gyd, wt, (N, C, H, W), K, R, stride, pad, dil)
+    torch.cuda.synchronize()
+    e = rel_err(dx, dx_ref)
+    assert e < 1e-2, "dgrad rel err %g" % e
+
+    dw = torch.zeros((K, R, R, C), dtype=torch.float32, device=cuda)
+    ops.conv_wgrad(xd, gyd, K, R, stride, pad, dil, dw)
+    torch.cuda.synchronize()
+    e = rel_err(dw.permute(0, 3, 1, 2), dw_ref)
+    assert e < 1e-2, "wgrad rel err %g" % e
+
+
+def test_conv_classifier_fp32_bias(cuda):
+    """1x1 classifier 256→19 with bias, fp32 NHWC output with channel stride 32 (head logits)"""
+    from torchseg_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    N, C, H, W, K = 2, 256, 16, 16, 19
+    x = bf16_round(torch.randn(N, C, H, W, generator=g))
+    w = bf16_round(torch.randn(K, C, 1, 1, generator=g) / 16)
+    b = torch.randn(K, generator=g)
+    y_ref = F.conv2d(x, w, b)
+    xd = ops.to_nhwc(x.to(cuda))
+    wb = w.to(cuda).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    y = ops.conv_fprop(xd, wb, K, 1, 1, 0, 1, bias=b.to(cuda), out_dtype=torch.float32, ocs=32)
+    assert ops.cs_of(y) == 32
+    assert rel_err(y, y_ref) < 1e-2
+
+
+def test_conv_dgrad_accumulate(cuda):
+    from torchseg_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    N, C, H, W, K = 2, 64, 16, 16, 64
+    w = bf16_round(torch.randn(K, C, 3, 3, generator=g) / 24)
+    gy = bf16_round(torch.randn(N, K, H, W, generator=g))
+    base = bf16_round(torch.randn(N, C, H, W, generator=g))
+    ref = F.conv_transpose2d(gy, w, None, 1, 1) + base
+    wk = w.to(cuda).permute(0, 2, 3, 1).contiguous()
+    wt = torch.empty((C, 3, 3, K), dtype=torch.bfloat16, device=cuda)
+    ops.call("tsb_pack_weight", ops.ptr(wk), K, 3, 3, C, None, ops.ptr(wt), ops.stream())
+    out = ops.to_nhwc(base.to(cuda))
+    ops.conv_dgrad(ops.to_nhwc(gy.to(cuda)), wt, (N, C, H, W), K, 3, 1, 1, 1, out=out, accumulate=True)
+    assert rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("HW", [(64, 64), (32, 96)])
+def test_stem_7x7(cuda, HW):
+    """7x7/2 stem through the space-to-depth pack (fprop + wgrad)"""
+    from torchseg_b200 import ops
+    H, W = HW
+    g = torch.Generator().manual_seed(3)
+    N, K = 2, 64
+    img = torch.randn(N, 3, H, W, generator=g)
+    w = bf16_round(torch.randn(K, 3, 7, 7, generator=g) / 12)
+    img_b = bf16_round(img)
+    gy = bf16_round(torch.randn(N, K, H // 2, W // 2, generator=g))
+    wr = w.clone().requires_grad_(True)
+    y_ref = F.conv2d(img_b, wr, None, 2, 3)
+    y_ref.backward(gy)
+    xs = ops.pack_image_s2d(img.to(cuda))
+    wk = w.to(cuda).permute(0, 2, 3, 1).contiguous()
+    wp = torch.empty((K, 4, 4, 16), dtype=torch.bfloat16, device=cuda)
+    ops.call("tsb_pack_stem_weight", ops.ptr(wk), K, ops.ptr(wp), ops.stream())
+    y = ops.nhwc_empty(N, K, H // 2, W // 2)
+    stats = torch.zeros(2, K, device=cuda)
+    ops.call("tsb_conv_stem_fprop", ops.ptr(xs), N, H, W, ops.ptr(wp), K, ops.ptr(y), K, ops.ptr(stats[0]), ops.ptr(stats[1]),
+             ops.stream())
+    torch.cuda.synchronize()
+    assert rel_err(y, y_ref) < 1e-2
+    dwp = torch.zeros((K, 4, 64), device=cuda)
+    ops.call("tsb_conv_stem_wgrad", ops.ptr(xs), N, H, W, ops.ptr(ops.to_nhwc(gy.to(cuda))), K, K, ops.ptr(dwp), ops.stream())
+    dw = torch.zeros((K, 7, 7, 3), device=cuda)
+    ops.call("tsb_unpack_stem_wgrad", ops.ptr(dwp), K, ops.ptr(dw), ops.stream())
+    torch.cuda.synchronize()
+    assert rel_err(dw.permute(0, 3, 1, 2), wr.grad) < 1e-2
+
+
+def test_conv_full_size_linearity(cuda):
+    """BASELINE-size layer (16 x 64 x 256 x 256, 3x3): size-independent property conv(a)+conv(b) == conv(a+b)
+    on exactly representable inputs, and agreement with cuDNN on a random crop of the output."""
+    from torchseg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    N, C, H, W, K = 16, 64, 256, 256, 64
+    a = torch.randint(-4, 5, (N, H, W, C), device=cuda, generator=g).to(torch.bfloat16).permute(0, 3, 1, 2)
+    b = torch.randint(-4, 5, (N, H, W, C), device=cuda, generator=g).to(torch.bfloat16).permute(0, 3, 1, 2)
+    w = (torch.randint(-2, 3, (K, 3, 3, C), device=cuda, generator=g).float() / 4)
+    wb = w.to(torch.bfloat16)
+    ya = ops.conv_fprop(a, wb, K, 3, 1, 1, 1).float()
+    yb = ops.conv_fprop(b, wb, K, 3, 1, 1, 1).float()
+    yab = ops.conv_fprop((a + b), wb, K, 3, 1, 1, 1).float()
+    assert torch.equal(ya + yb, yab)  # all partial sums are small integers / 4: exact in fp32 and bf16
+    ref = F.conv2d(a[:2].float(), w.permute(0, 3, 1, 2), None, 1, 1)
+    assert torch.equal(ya[:2], ref)

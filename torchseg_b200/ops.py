@@ -1,0 +1,541 @@
+"""torch.autograd.Function wrappers around the libtsb C ABI (include/tsb.h).
+
+PyTorch drives only the graph, the memory and the streams; every op below runs a hand-written sm_100a
+kernel. Activations are bf16 tensors of LOGICAL shape [N,C,H,W] stored NHWC (`nhwc_empty`), possibly a
+channel slice of a wider buffer (channel stride `cs`). There is no CPU / ATen fallback: without a GPU or
+without libtsb.so these functions raise.
+"""
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, ConvShape, call, ptr, stream
+
+import ctypes
+
+_BF = torch.bfloat16
+
+
+# --------------------------------------------------------------------------------------------------
+# tensor helpers
+# --------------------------------------------------------------------------------------------------
+def nhwc_empty(N, C, H, W, dtype=_BF, device="cuda", cs=None):
+    """logical [N,C,H,W] view of a fresh NHWC buffer (channel stride cs >= C)"""
+    cs = C if cs is None else cs
+    buf = torch.empty((N, H, W, cs), dtype=dtype, device=device)
+    return buf[..., :C].permute(0, 3, 1, 2)
+
+
+def nhwc_zeros(N, C, H, W, dtype=_BF, device="cuda", cs=None):
+    cs = C if cs is None else cs
+    buf = torch.zeros((N, H, W, cs), dtype=dtype, device=device)
+    return buf[..., :C].permute(0, 3, 1, 2)
+
+
+def cs_of(t):
+    """channel stride of an NHWC-backed logical NCHW tensor; validates the layout"""
+    assert t.dim() == 4, "expected a 4-D tensor"
+    N, C, H, W = t.shape
+    s = t.stride()
+    if C > 1 and s[1] != 1:
+        raise ValueError("tensor is not NHWC-backed (channel stride %d); use to_nhwc()" % s[1])
+    cs = s[3]
+    if (W > 1 and s[2] != W * cs) or (H * W > 1 and N > 1 and s[0] != H * W * cs):
+        raise ValueError("tensor is not a dense NHWC buffer: shape %s strides %s" % (tuple(t.shape), s))
+    return cs
+
+
+def to_nhwc(t, dtype=_BF):
+    """any [N,C,H,W] tensor → NHWC-backed logical NCHW tensor of `dtype` (ATen copy; boundary only)"""
+    N, C, H, W = t.shape
+    out = nhwc_empty(N, C, H, W, dtype=dtype, device=t.device)
+    out.copy_(t)
+    return out
+
+
+def _krsc_ptr(w):
+    """pointer to a dense [K,R,S,C] fp32 buffer for conv weight w ([K,C,R,S] logical)"""
+    wp = w.permute(0, 2, 3, 1)
+    if not wp.is_contiguous():
+        raise ValueError("conv weight must be channels_last (KRSC); call torchseg_b200.prepare_model(model)")
+    return wp
+
+
+def conv_out_size(H, k, stride, pad, dil):
+    return (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def make_shape(N, H, W, C, K, R, stride, pad, dil):
+    P = conv_out_size(H, R, stride, pad, dil)
+    Q = conv_out_size(W, R, stride, pad, dil)
+    return ConvShape(N, H, W, C, K, R, R, stride, pad, dil, P, Q)
+
+
+# --------------------------------------------------------------------------------------------------
+# bf16 weight packs, cached per optimiser step
+# --------------------------------------------------------------------------------------------------
+class _PackCache:
+    def __init__(self):
+        self.step = 0
+        self.cache = {}
+
+    def invalidate(self):
+        self.step += 1
+        self.cache.clear()
+
+    def get(self, w, want_t, pad_k=None, stem=False):
+        key = (w.data_ptr(), bool(want_t), pad_k, stem, w._version)
+        hit = self.cache.get(key)
+        if hit is not None:
+            return hit
+        K, C, R, S = w.shape
+        if stem:
+            wp = torch.empty((K, 4, 4, 16), dtype=_BF, device=w.device)
+            call("tsb_pack_stem_weight", ptr(_krsc_ptr(w)), K, ptr(wp), stream())
+            out = (wp, None)
+        else:
+            src = _krsc_ptr(w)
+            if pad_k is not None and pad_k != K:  # classifier: pad K (19) up to 64 rows of zeros
+                padded = torch.zeros((pad_k, R, S, C), dtype=torch.float32, device=w.device)
+                padded[:K].copy_(src)
+                src, K = padded, pad_k
+            wb = torch.empty((K, R, S, C), dtype=_BF, device=w.device)
+            wt = torch.empty((C, R, S, K), dtype=_BF, device=w.device) if want_t else None
+            call("tsb_pack_weight", ptr(src), K, R, S, C, ptr(wb), ptr(wt), stream())
+            out = (wb, wt)
+        self.cache[key] = out
+        return out
+
+
+pack_cache = _PackCache()
+
+# process group for SyncBN statistics (set by apex_shim.parallel.SyncBatchNorm / DistributedDataParallel)
+_sync = {"group": None, "world": 1}
+
+
+def set_sync_group(group, world):
+    _sync["group"], _sync["world"] = group, world
+
+
+def _allreduce_stats(buf):
+    if _sync["world"] > 1:
+        import torch.distributed as dist
+        dist.all_reduce(buf, group=_sync["group"])
+
+
+# --------------------------------------------------------------------------------------------------
+# low-level conv calls
+# --------------------------------------------------------------------------------------------------
+def conv_fprop(x, wb, K, R, stride, pad, dil, bias=None, out_dtype=_BF, out=None, ocs=None, stats=None):
+    N, C, H, W = x.shape
+    shp = make_shape(N, H, W, C, K, R, stride, pad, dil)
+    if out is None:
+        ocs_alloc = ocs if ocs is not None else (K + 7) // 8 * 8
+        out = nhwc_empty(N, K, shp.P, shp.Q, dtype=out_dtype, device=x.device, cs=ocs_alloc)
+    s1 = s2 = None
+    if stats is not None:
+        s1, s2 = stats[0], stats[1]
+    call("tsb_conv2d_fprop", ctypes.byref(shp), ptr(x), cs_of(x), ptr(wb), ptr(bias), ptr(out), _lib.dt(out), cs_of(out),
+         ptr(s1), ptr(s2), stream())
+    return out
+
+
+def conv_dgrad(dy, wt, xshape, K, R, stride, pad, dil, out=None, accumulate=False):
+    N, C, H, W = xshape
+    shp = make_shape(N, H, W, C, K, R, stride, pad, dil)
+    if out is None:
+        out = nhwc_empty(N, C, H, W, device=dy.device)
+    call("tsb_conv2d_dgrad", ctypes.byref(shp), ptr(dy), cs_of(dy), ptr(wt), ptr(out), cs_of(out), int(accumulate), stream())
+    return out
+
+
+def conv_wgrad(x, dy, K, R, stride, pad, dil, dw_krsc):
+    N, C, H, W = x.shape
+    shp = make_shape(N, H, W, C, K, R, stride, pad, dil)
+    call("tsb_conv2d_wgrad", ctypes.byref(shp), ptr(x), cs_of(x), ptr(dy), cs_of(dy), ptr(dw_krsc), stream())
+
+
+def _new_wgrad(w):
+    """zeroed gradient with the parameter's (KRSC) strides: returns (logical view, dense KRSC tensor)"""
+    K, C, R, S = w.shape
+    g = torch.zeros((K, R, S, C), dtype=torch.float32, device=w.device)
+    return g.permute(0, 3, 1, 2), g
+
+
+# --------------------------------------------------------------------------------------------------
+# Conv + (Sync)BatchNorm(train) + residual + ReLU  — ConvBnRelu / BasicBlock tail
+# --------------------------------------------------------------------------------------------------
+class ConvBNActFn(torch.autograd.Function):
+    """y = act(BN_train(conv(x, w)) + residual).
+
+    Replaces ConvBnRelu.forward (/root/reference/furnace/seg_opr/seg_oprs.py:39-46) and the conv→bn→(+res)→relu
+    groups of BasicBlock.forward (/root/reference/furnace/base_model/resnet.py:33-53). The conv epilogue emits
+    the per-channel Σ/Σ² (BN statistics), tsb_bn_finalize turns them into scale/shift (and updates the
+    running stats), tsb_bn_apply normalises (+residual, +ReLU) in one pass.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, residual, running_mean, running_var, stride, pad, dil, relu, eps, momentum,
+                training, stem):
+        K = w.shape[0]
+        R = w.shape[2]
+        dev = x.device
+        if stem:
+            N, _, H2, WP = x.shape  # xs2d [N, 16, H/2, W/2+4]
+            H, W = H2 * 2, (WP - 4) * 2
+            P, Q = H2, WP - 4
+        else:
+            N, C, H, W = x.shape
+            P, Q = conv_out_size(H, R, stride, pad, dil), conv_out_size(W, R, stride, pad, dil)
+        count = float(N * P * Q) * _sync["world"]
+        if training:
+            stats = torch.zeros((2, K), dtype=torch.float32, device=dev)
+        else:
+            stats = None
+        raw = nhwc_empty(N, K, P, Q, device=dev)
+        if stem:
+            wp, _ = pack_cache.get(w, False, stem=True)
+            call("tsb_conv_stem_fprop", ptr(x), N, H, W, ptr(wp), K, ptr(raw), K, ptr(stats[0]) if training else None,
+                 ptr(stats[1]) if training else None, stream())
+        else:
+            wb, _ = pack_cache.get(w, False)
+            conv_fprop(x, wb, K, R, stride, pad, dil, out=raw, stats=stats)
+        aux = torch.empty((4, K), dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
+        if training:
+            _allreduce_stats(stats)
+            call("tsb_bn_finalize", ptr(stats[0]), ptr(stats[1]), count, K, ptr(gamma), ptr(beta), eps, momentum,
+                 ptr(aux[0]), ptr(aux[1]), ptr(aux[2]), ptr(aux[3]), ptr(running_mean), ptr(running_var), stream())
+        else:
+            # eval: scale/shift from the running statistics (sum := mean*1, sumsq := var + mean^2, count 1)
+            s = torch.stack([running_mean, running_var + running_mean * running_mean]).contiguous()
+            call("tsb_bn_finalize", ptr(s[0]), ptr(s[1]), 1.0, K, ptr(gamma), ptr(beta), eps, 0.0, ptr(aux[0]),
+                 ptr(aux[1]), ptr(aux[2]), ptr(aux[3]), None, None, stream())
+        y = nhwc_empty(N, K, P, Q, device=dev)
+        call("tsb_bn_apply", ptr(raw), K, ptr(aux[2]), ptr(aux[3]), ptr(residual), cs_of(residual) if residual is not None else 0,
+             int(relu), ptr(y), K, N * P * Q, K, stream())
+        ctx.save_for_backward(x, w, gamma, raw, y, aux)
+        ctx.cfg = (stride, pad, dil, relu, stem, residual is not None, count, training)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, gamma, raw, y, aux = ctx.saved_tensors
+        stride, pad, dil, relu, stem, has_res, count, training = ctx.cfg
+        assert training, "backward through eval-mode BN is not supported"
+        K = w.shape[0]
+        R = w.shape[2]
+        N, _, P, Q = raw.shape
+        dev = dy.device
+        npix = N * P * Q
+        if dy.dtype != _BF or dy.stride(1) != 1:
+            dy = to_nhwc(dy)
+        red = torch.zeros((2, K), dtype=torch.float32, device=dev)
+        call("tsb_bn_bwd_reduce", ptr(dy), cs_of(dy), ptr(y), K, ptr(raw), K, ptr(aux[0]), ptr(aux[1]), int(relu), npix, K,
+             ptr(red[0]), ptr(red[1]), stream())
+        # dgamma = Σ dz·x̂, dbeta = Σ dz are LOCAL sums (the DDP all-reduce averages parameter grads);
+        # the dx formula needs the GLOBAL sums under SyncBN.
+        dgamma = red[1].clone()
+        dbeta = red[0].clone()
+        _allreduce_stats(red)
+        draw = nhwc_empty(N, K, P, Q, device=dev)
+        dres = nhwc_empty(N, K, P, Q, device=dev) if has_res else None
+        call("tsb_bn_bwd_apply", ptr(dy), cs_of(dy), ptr(y), K, ptr(raw), K, ptr(aux[0]), ptr(aux[1]), ptr(gamma), ptr(red[0]),
+             ptr(red[1]), count, int(relu), ptr(draw), K, ptr(dres), K if has_res else 0, npix, K, stream())
+        dw_view, dw = _new_wgrad(w)
+        dx = None
+        if stem:
+            H, W = P * 2, Q * 2
+            dwp = torch.zeros((K, 4, 64), dtype=torch.float32, device=dev)
+            call("tsb_conv_stem_wgrad", ptr(x), N, H, W, ptr(draw), K, K, ptr(dwp), stream())
+            call("tsb_unpack_stem_wgrad", ptr(dwp), K, ptr(dw), stream())
+        else:
+            conv_wgrad(x, draw, K, R, stride, pad, dil, dw)
+            if ctx.needs_input_grad[0]:
+                _, wt = pack_cache.get(w, True)
+                dx = conv_dgrad(draw, wt, x.shape, K, R, stride, pad, dil)
+        return dx, dw_view, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
+
+
+class ConvFn(torch.autograd.Function):
+    """plain convolution (+bias), bf16 or fp32 output with channel stride `ocs` — the 1x1 classifier heads
+    (bisenet network.py:156-161) and the BN-free SE convs of FeatureFusion (seg_oprs.py:224-229)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad, dil, out_f32, ocs):
+        K, C, R, _ = w.shape
+        wb, _ = pack_cache.get(w, False)
+        y = conv_fprop(x, wb, K, R, stride, pad, dil, bias=bias, out_dtype=torch.float32 if out_f32 else _BF, ocs=ocs)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad, dil, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        stride, pad, dil, has_bias = ctx.cfg
+        K, C, R, _ = w.shape
+        N, _, P, Q = dy.shape
+        dev = dy.device
+        # dgrad needs the GEMM-K (= out channels) padded to a multiple of 64 in a bf16 NHWC buffer
+        Kp = (K + 63) // 64 * 64
+        if dy.dtype == _BF and dy.stride(1) == 1 and cs_of(dy) >= Kp and K == Kp:
+            dyb = dy
+        else:
+            dyb = nhwc_zeros(N, Kp, P, Q, device=dev)
+            if dy.stride(1) == 1 and K % 8 == 0:
+                call("tsb_cast_scale", ptr(dy), _lib.dt(dy), cs_of(dy), ptr(dyb), BF16, Kp, N * P * Q, K, None, stream())
+            else:
+                dyb[:, :K].copy_(dy)
+        dw_view, dw = _new_wgrad(w)
+        conv_wgrad(x, dyb[:, :K], K, R, stride, pad, dil, dw)
+        db = None
+        if has_bias:
+            db = torch.zeros((K,), dtype=torch.float32, device=dev)
+            call("tsb_bias_grad", ptr(dyb), Kp, N * P * Q, K, ptr(db), stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wt = pack_cache.get(w, True, pad_k=Kp)
+            dx = conv_dgrad(dyb, wt, x.shape, Kp, R, stride, pad, dil)
+        return dx, dw_view, db, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# pooling / resize / attention scale
+# --------------------------------------------------------------------------------------------------
+class MaxPool3x3S2Fn(torch.autograd.Function):
+    """nn.MaxPool2d(3, 2, 1) — /root/reference/furnace/base_model/resnet.py:132"""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, C, H, W = x.shape
+        P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = nhwc_empty(N, C, P, Q, device=x.device)
+        call("tsb_maxpool3x3s2_fwd", ptr(x), cs_of(x), ptr(y), C, N, C, H, W, stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, C, H, W = x.shape
+        if dy.dtype != _BF or dy.stride(1) != 1:
+            dy = to_nhwc(dy)
+        dx = nhwc_empty(N, C, H, W, device=x.device)
+        call("tsb_maxpool3x3s2_bwd", ptr(x), cs_of(x), ptr(dy), cs_of(dy), ptr(dx), C, N, C, H, W, stream())
+        return dx
+
+
+class AdaptiveAvgPoolFn(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(S) — seg_oprs.py:200,223; bisenet network.py:35; pspnet network.py:83.
+    Output bf16 [N,C,S,S] (NHWC)."""
+
+    @staticmethod
+    def forward(ctx, x, S):
+        N, C, H, W = x.shape
+        o32 = torch.empty((N, S, S, C), dtype=torch.float32, device=x.device)
+        call("tsb_adaptive_avgpool_fwd", ptr(x), cs_of(x), N, C, H, W, S, ptr(o32), stream())
+        out = nhwc_empty(N, C, S, S, device=x.device)
+        call("tsb_cast_scale", ptr(o32), F32, C, ptr(out), BF16, C, N * S * S, C, None, stream())
+        ctx.shape = (N, C, H, W, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W, S = ctx.shape
+        if dy.stride(1) != 1:
+            dy = to_nhwc(dy, dy.dtype)
+        d32 = torch.empty((N, S, S, C), dtype=torch.float32, device=dy.device)
+        call("tsb_cast_scale", ptr(dy), _lib.dt(dy), cs_of(dy), ptr(d32), F32, C, N * S * S, C, None, stream())
+        dx = nhwc_empty(N, C, H, W, device=dy.device)
+        call("tsb_adaptive_avgpool_bwd", ptr(d32), N, C, H, W, S, ptr(dx), C, 0, stream())
+        return dx, None
+
+
+class BilinearFn(torch.autograd.Function):
+    """F.interpolate(mode='bilinear', align_corners=True) — bisenet network.py:82-84,93-94"""
+
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        N, C, Hi, Wi = x.shape
+        y = nhwc_empty(N, C, Ho, Wo, device=x.device)
+        call("tsb_bilinear_fwd", ptr(x), _lib.dt(x), cs_of(x), ptr(y), BF16, C, N, C, Hi, Wi, Ho, Wo, stream())
+        ctx.shape = (N, C, Hi, Wi, Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, Hi, Wi, Ho, Wo = ctx.shape
+        if dy.dtype != _BF or dy.stride(1) != 1:
+            dy = to_nhwc(dy)
+        dx = nhwc_empty(N, C, Hi, Wi, device=dy.device)
+        call("tsb_bilinear_bwd", ptr(dy), BF16, cs_of(dy), ptr(dx), BF16, C, N, C, Hi, Wi, Ho, Wo, 0, stream())
+        return dx, None, None
+
+
+class ChanScaleFn(torch.autograd.Function):
+    """y = x * (base + sigmoid(a)) + add.  ARM: base 0 (+ the caller's `fm += last_fm`, bisenet network.py:91-92);
+    FFM: base 1 (fm + fm*se, seg_oprs.py:237). `a` is the bf16 [N,C,1,1] pre-sigmoid attention logit."""
+
+    @staticmethod
+    def forward(ctx, x, a, add, base):
+        N, C, H, W = x.shape
+        a32 = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        call("tsb_cast_scale", ptr(a), _lib.dt(a), cs_of(a), ptr(a32), F32, C, N, C, None, stream())
+        y = nhwc_empty(N, C, H, W, device=x.device)
+        call("tsb_chan_scale_fwd", ptr(x), cs_of(x), ptr(a32), float(base), ptr(add), cs_of(add) if add is not None else 0,
+             ptr(y), C, N, H * W, C, stream())
+        ctx.save_for_backward(x, a32)
+        ctx.cfg = (base, add is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a32 = ctx.saved_tensors
+        base, has_add = ctx.cfg
+        N, C, H, W = x.shape
+        if dy.dtype != _BF or dy.stride(1) != 1:
+            dy = to_nhwc(dy)
+        dx = nhwc_empty(N, C, H, W, device=x.device)
+        da32 = torch.zeros((N, C), dtype=torch.float32, device=x.device)
+        call("tsb_chan_scale_bwd", ptr(dy), cs_of(dy), ptr(x), cs_of(x), ptr(a32), float(base), ptr(dx), C, ptr(da32), N,
+             H * W, C, stream())
+        da = nhwc_empty(N, C, 1, 1, device=x.device)
+        call("tsb_cast_scale", ptr(da32), F32, C, ptr(da), BF16, C, N, C, None, stream())
+        return dx, da, (dy if has_add else None), None
+
+
+class ConcatFn(torch.autograd.Function):
+    """torch.cat([x1, x2], dim=1) (FeatureFusion, seg_oprs.py:234) as two strided copies into one NHWC buffer;
+    backward hands out channel-slice views (no copy)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2):
+        N, C1, H, W = x1.shape
+        C2 = x2.shape[1]
+        out = nhwc_empty(N, C1 + C2, H, W, device=x1.device)
+        npix = N * H * W
+        call("tsb_cast_scale", ptr(x1), BF16, cs_of(x1), ptr(out), BF16, C1 + C2, npix, C1, None, stream())
+        call("tsb_cast_scale", ptr(x2), BF16, cs_of(x2), ptr(out[:, C1:]), BF16, C1 + C2, npix, C2, None, stream())
+        ctx.c1 = C1
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy.dtype != _BF or dy.stride(1) != 1:
+            dy = to_nhwc(dy)
+        return dy[:, :ctx.c1], dy[:, ctx.c1:]
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        N, C, H, W = a.shape
+        y = nhwc_empty(N, C, H, W, device=a.device)
+        call("tsb_add", ptr(a), cs_of(a), ptr(b), cs_of(b), ptr(y), C, N * H * W, C, stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+# --------------------------------------------------------------------------------------------------
+# image packing (network input boundary)
+# --------------------------------------------------------------------------------------------------
+def pack_image_s2d(img):
+    """NCHW fp32 image → [N,16,H/2,W/2+4] bf16 (NHWC) operand of the 7x7/2 stems"""
+    N, C, H, W = img.shape
+    assert C == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    out = nhwc_empty(N, 16, H // 2, W // 2 + 4, device=img.device)
+    call("tsb_pack_image_s2d", ptr(img), N, H, W, ptr(out), stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# OHEM cross-entropy
+# --------------------------------------------------------------------------------------------------
+def _ohem_forward(pt_call, n, labels, ignore_label, thresh, min_kept, class_weight, dev):
+    state = torch.empty((_lib.OHEM_STATE_WORDS,), dtype=torch.int32, device=dev)
+    p = torch.empty((n,), dtype=torch.float32, device=dev)
+    nll = torch.empty((n,), dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    call("tsb_ohem_begin", ptr(state), stream())
+    pt_call(p, nll, state)
+    call("tsb_ohem_select", ptr(p), n, int(min_kept), float(thresh), ptr(state), stream())
+    call("tsb_ohem_loss", ptr(p), ptr(nll), ptr(labels), n, int(ignore_label), ptr(class_weight), ptr(state), ptr(loss),
+         stream())
+    return loss, p, state
+
+
+class OhemCEFn(torch.autograd.Function):
+    """ProbOhemCrossEntropy2d.forward on MATERIALISED logits [N,C,H,W] (any strides, fp32/bf16) —
+    /root/reference/furnace/seg_opr/loss_opr.py:68-98."""
+
+    @staticmethod
+    def forward(ctx, pred, target, ignore_label, thresh, min_kept, class_weight):
+        N, C, H, W = pred.shape
+        target = target.contiguous()
+        sn, sc, sy, sx = pred.stride()
+        dtp = _lib.dt(pred)
+
+        def pt(p, nll, state):
+            call("tsb_ohem_ptarget", ptr(pred), dtp, sn, sc, sy, sx, ptr(target), N, C, H, W, int(ignore_label),
+                 float(thresh), ptr(p), ptr(nll), ptr(state), stream())
+
+        loss, p, state = _ohem_forward(pt, N * H * W, target, ignore_label, thresh, min_kept, class_weight, pred.device)
+        ctx.save_for_backward(pred, target, p, state, class_weight if class_weight is not None else torch.empty(0))
+        ctx.cfg = (ignore_label, class_weight is not None)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, p, state, cw = ctx.saved_tensors
+        ignore_label, has_cw = ctx.cfg
+        N, C, H, W = pred.shape
+        sn, sc, sy, sx = pred.stride()
+        d = torch.empty_strided(pred.shape, pred.stride(), dtype=pred.dtype, device=pred.device)
+        g = g.to(torch.float32).contiguous()
+        call("tsb_ohem_grad", ptr(pred), _lib.dt(pred), sn, sc, sy, sx, ptr(target), ptr(p), N, C, H, W, int(ignore_label),
+             ptr(cw) if has_cw else None, ptr(state), ptr(g), ptr(d), stream())
+        return d, None, None, None, None, None
+
+
+class OhemUpCEFn(torch.autograd.Function):
+    """Fused head tail: bilinear x`scale` upsample (align_corners) of the LOW-res fp32 NHWC logits +
+    ProbOhemCrossEntropy2d; the full-resolution logits are never written (bisenet network.py:104-108,163-166)."""
+
+    @staticmethod
+    def forward(ctx, lo, target, H, W, num_classes, ignore_label, thresh, min_kept, class_weight):
+        N, _, h, w = lo.shape
+        assert lo.dtype == torch.float32
+        target = target.contiguous()
+        cs = cs_of(lo)
+
+        def pt(p, nll, state):
+            call("tsb_ohem_ptarget_up", ptr(lo), cs, h, w, ptr(target), N, num_classes, H, W, int(ignore_label),
+                 float(thresh), ptr(p), ptr(nll), ptr(state), stream())
+
+        loss, p, state = _ohem_forward(pt, N * H * W, target, ignore_label, thresh, min_kept, class_weight, lo.device)
+        ctx.save_for_backward(lo, target, p, state, class_weight if class_weight is not None else torch.empty(0))
+        ctx.cfg = (H, W, num_classes, ignore_label, class_weight is not None)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lo, target, p, state, cw = ctx.saved_tensors
+        H, W, C, ignore_label, has_cw = ctx.cfg
+        N, Cl, h, w = lo.shape
+        cs = cs_of(lo)
+        d = nhwc_zeros(N, Cl, h, w, dtype=torch.float32, device=lo.device, cs=cs)
+        g = g.to(torch.float32).contiguous()
+        call("tsb_ohem_grad_up", ptr(lo), cs, h, w, ptr(target), ptr(p), N, C, H, W, int(ignore_label),
+             ptr(cw) if has_cw else None, ptr(state), ptr(g), ptr(d), stream())
+        return d, None, None, None, None, None, None, None, None
+
+
+def ohem_state_dict(state):
+    """decode the OHEM state words (host sync) — for tests / logging"""
+    s = state.cpu()
+    f = s.view(torch.float32)
+    return dict(num_valid=int(s[_lib.OHEM_ST_NUM_VALID]), count_le=int(s[_lib.OHEM_ST_COUNT_LE]),
+                active=bool(s[_lib.OHEM_ST_ACTIVE]), T=float(f[_lib.OHEM_ST_THRESH]), kept=int(s[_lib.OHEM_ST_KEPT]),
+                loss=float(f[_lib.OHEM_ST_LOSS]))
