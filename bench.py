@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the BiSeNet-R18 training step (1024x1024, 19 classes, bf16, batch 16/GPU, OHEM).
+
+    python bench.py --gpus N --steps K --warmup W            # B200-native path (libtsb)
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU arm (oracle port on host cores)
+
+One "step" = zero_grad → forward (3 OHEM losses) → backward → gradient all-reduce (N>1) → fused SGD step, i.e.
+/root/reference/model/bisenet/cityscapes.bisenet.R18/train.py:116-142 on synthetic data.
+Prints ONE JSON line (rank 0). See the task contract for the keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H = W = 1024
+NUM_CLASSES = 19
+BATCH_PER_GPU = 16
+STEP_GFLOP_PER_IMG = 338.1   # 3 x 116.00 - 2 x 4.933 (conv FLOPs, fprop+dgrad+wgrad)
+METRIC = "images/sec training step (1024x1024, 19-class)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured (sustained)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ data
+def synth_batch(n, h, w, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    imgs = torch.randn(n, 3, h, w, generator=g)
+    labels = torch.randint(0, NUM_CLASSES, (n, h, w), generator=g, dtype=torch.int64)
+    labels[:, : h // 10, :] = 255  # deterministic ~10 % ignore band
+    if pin and torch.cuda.is_available():
+        imgs, labels = imgs.pin_memory(), labels.pin_memory()
+    return imgs.to(device), labels.to(device)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------ model
+def build_b200(device, world):
+    import torchseg_b200
+    from torchseg_b200 import optim
+    from torchseg_b200.apex.parallel import DistributedDataParallel, SyncBatchNorm
+    from torchseg_b200.engine.lr_policy import PolyLR
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.seg_opr.loss_opr import ProbOhemCrossEntropy2d
+    from torchseg_b200.utils.init_func import init_weight, group_weight
+    norm = SyncBatchNorm if world > 1 else torch.nn.BatchNorm2d
+    min_kept = BATCH_PER_GPU * H * W // 16  # train.py:48-49
+    crit = ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=False)
+    torch.manual_seed(12345)
+    model = BiSeNet(NUM_CLASSES, True, crit, None, norm)
+    init_weight(model.business_layer, torch.nn.init.kaiming_normal_, norm, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+    model.to(device)
+    torchseg_b200.prepare_model(model)
+    base_lr = 1e-2
+    groups = group_weight([], model.context_path, norm, base_lr)
+    for m in (model.spatial_path, model.global_context, model.arms, model.refines, model.heads, model.ffm):
+        groups = group_weight(groups, m, norm, base_lr * 10)
+    opt = optim.SGD(groups, lr=base_lr, momentum=0.9, weight_decay=5e-4)
+    lr_policy = PolyLR(base_lr, 0.9, 80 * 1000)
+    ddp = DistributedDataParallel(model) if world > 1 else None
+    model.train()
+    return model, ddp, opt, lr_policy
+
+
+def train_step(model, ddp, opt, lr_policy, it, imgs, gts):
+    opt.zero_grad()
+    loss = (ddp or model)(imgs, gts)
+    lr = lr_policy.get_lr(it)
+    for i, g in enumerate(opt.param_groups):
+        g['lr'] = lr if i < 2 else lr * 10  # train.py:136-139
+    loss.backward()
+    if ddp is not None:
+        ddp.finish_reduce()
+    opt.step()
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_steps(n, h, w, steps, warmup, threads):
+    """The reference algorithm (oracle/torch_ref.py restatement, fp32, NCHW, stock torch.nn lowering) driving the
+    same zero_grad → forward(loss) → backward → SGD step sequence on the host CPU."""
+    from oracle import torch_ref
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.utils.init_func import init_weight
+    torch.set_num_threads(threads)
+    torch.manual_seed(12345)
+    shell = BiSeNet(NUM_CLASSES, True, None, None, torch.nn.BatchNorm2d)
+    init_weight(shell.business_layer, torch.nn.init.kaiming_normal_, torch.nn.BatchNorm2d, 1e-5, 0.1, mode='fan_in',
+                nonlinearity='relu')
+    sd = {k: v.detach().clone() for k, v in shell.state_dict().items()}
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+            params.append(v)
+    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    imgs, gts = synth_batch(n, h, w, 7)
+    min_kept = n * h * w // 16
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _ = torch_ref.bisenet_r18_loss(imgs, gts, sd, min_kept)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return n * len(times) / sum(times), float(loss)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n, hw = 2, 1024
+    ips, _ = cpu_reference_steps(n, hw, hw, args.steps, max(1, min(args.warmup, 1)), threads)
+    sample = "oracle port of the reference step (fp32 NCHW torch.nn lowering), batch %d @ %dx%d, %d timed steps" % (
+        n, hw, hw, args.steps)
+    line = dict(impl="reference", metric=METRIC, value=ips, unit="images/sec", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1000.0 * n / ips, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload="BiSeNet-R18 train step 1024x1024 19-class OHEM", batch_per_step=n, device="host CPU"),
+                cpu_baseline=dict(value=ips, unit="images/sec", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=ips, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def main():
+    global BATCH_PER_GPU
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (BASELINE: 16)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from torchseg_b200 import _lib, ops
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl b200) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", init_method="env://", device_id=device)
+    warmup = max(3, args.warmup)
+    BATCH_PER_GPU = args.batch
+
+    model, ddp, opt, lr_policy = build_b200(device, world)
+    host_imgs, host_gts = synth_batch(BATCH_PER_GPU, H, W, 100 + rank, pin=True)
+    dev_imgs, dev_gts = host_imgs.to(device), host_gts.to(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    it = 0
+    for _ in range(warmup):
+        loss = train_step(model, ddp, opt, lr_policy, it, dev_imgs, dev_gts)
+        it += 1
+    # ---------------- timed region 1: inputs resident in HBM; conv launches bracketed by CUDA events
+    ops.conv_prof.enable()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            loss = train_step(model, ddp, opt, lr_policy, it, dev_imgs, dev_gts)
+            it += 1
+        e1.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    prof = ops.conv_prof.collect()
+    ops.conv_prof.disable()
+    final_loss = float(loss.item())
+    # ---------------- timed region 2: end to end through the public API with HOST buffers
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        imgs = host_imgs.cuda(device, non_blocking=True)   # train.py:123-124
+        gts = host_gts.cuda(device, non_blocking=True)
+        loss = train_step(model, ddp, opt, lr_policy, it, imgs, gts)
+        it += 1
+        _ = loss.item()                                     # train.py:146 (per-iteration host read of the loss)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+
+    if rank == 0:
+        peaks = load_peaks()
+        n_img = BATCH_PER_GPU * world * args.steps
+        value = n_img / (ms / 1000.0)
+        e2e_v = n_img / (ms_e2e / 1000.0)
+        conv_tf = prof["flops"] / max(prof["ms"], 1e-9) / 1e9  # TFLOP/s over all conv launches of the region
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BiSeNet-R18 train step, 1024x1024, 19-class, OHEM (BASELINE configs[1])",
+                       "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
+                       "sync_bn": world > 1, "optimizer": "fused flat SGD (momentum 0.9, wd 5e-4, poly LR)",
+                       "l2_policy": "inputs larger than L2 (activations >> 126 MB per step), no explicit flush",
+                       "final_loss": final_loss,
+                       "step_conv_gflop_per_img": STEP_GFLOP_PER_IMG,
+                       "frac_of_conv_flop_roofline": value / world * STEP_GFLOP_PER_IMG / 1e3 / peaks["tflops"]},
+            "e2e": {"value": e2e_v, "unit": "images/sec",
+                    "h2d_bytes_per_step": int(host_imgs.numel() * 4 + host_gts.numel() * 8), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": conv_tf / peaks["tflops"], "traffic": None,
+                         "kernel": "igemm_kmajor_kernel + wgrad_mnmajor_kernel (all conv fprop/dgrad/wgrad launches)",
+                         "launches": prof["launches"], "kernel_ms_per_step": prof["ms"] / args.steps,
+                         "peak_source": peaks["src"]},
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            ips, _ = cpu_reference_steps(2, 512, 512, 2, 1, threads)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port",
+                                    "sample": "oracle port of the reference step, batch 2 @ 512x512, 1 warm-up + 2 timed steps"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

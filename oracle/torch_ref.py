@@ -12,6 +12,37 @@ import torch.nn.functional as F
 
 
 # --------------------------------------------------------------------------------------------------
+# optional bf16-storage emulation: the SAME fp32 math, but values are rounded to bf16 (forward AND the
+# gradient flowing back) at the points where the B200 path stores bf16 — conv weights, raw conv outputs,
+# activations, pooled / resized maps. Separates "kernel bug" from "bf16 storage policy" in end-to-end tests.
+# --------------------------------------------------------------------------------------------------
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+_EMULATE = {"on": False}
+
+
+def set_bf16_emulation(on):
+    _EMULATE["on"] = bool(on)
+
+
+def q(t):
+    return _RoundBF16.apply(t) if _EMULATE["on"] else t
+
+
+def qw(w):
+    """weights are rounded in the forward only (the fp32 master weight receives the fp32 gradient)"""
+    return (w + (w.to(torch.bfloat16).to(torch.float32) - w).detach()) if _EMULATE["on"] else w
+
+
+# --------------------------------------------------------------------------------------------------
 # ProbOhemCrossEntropy2d.forward — /root/reference/furnace/seg_opr/loss_opr.py:68-98
 # (with `1 - mask` → `~mask`, the torch>=1.2 shim of SURVEY.md App. C2)
 # --------------------------------------------------------------------------------------------------
@@ -75,31 +106,31 @@ def _bn(x, sd, prefix, eps, momentum, training, stats=None):
 def conv_bn_relu(x, sd, prefix, stride, pad, dilation=1, has_bn=True, has_relu=True, eps=1e-5, momentum=0.1,
                  training=True, stats=None):
     """ConvBnRelu.forward — /root/reference/furnace/seg_opr/seg_oprs.py:39-46"""
-    x = F.conv2d(x, sd[prefix + ".conv.weight"], sd.get(prefix + ".conv.bias"), stride, pad, dilation)
+    x = q(F.conv2d(x, qw(sd[prefix + ".conv.weight"]), sd.get(prefix + ".conv.bias"), stride, pad, dilation))
     if has_bn:
         x = _bn(x, sd, prefix + ".bn", eps, momentum, training, stats)
     if has_relu:
         x = F.relu(x)
-    return x
+    return q(x)
 
 
 def basic_block(x, sd, prefix, stride, has_down, eps, momentum, training, stats=None):
     """BasicBlock.forward — /root/reference/furnace/base_model/resnet.py:33-53"""
-    out = F.conv2d(x, sd[prefix + ".conv1.weight"], None, stride, 1)
-    out = F.relu(_bn(out, sd, prefix + ".bn1", eps, momentum, training, stats))
-    out = F.conv2d(out, sd[prefix + ".conv2.weight"], None, 1, 1)
+    out = q(F.conv2d(x, qw(sd[prefix + ".conv1.weight"]), None, stride, 1))
+    out = q(F.relu(_bn(out, sd, prefix + ".bn1", eps, momentum, training, stats)))
+    out = q(F.conv2d(out, qw(sd[prefix + ".conv2.weight"]), None, 1, 1))
     out = _bn(out, sd, prefix + ".bn2", eps, momentum, training, stats)
     residual = x
     if has_down:
-        residual = F.conv2d(x, sd[prefix + ".downsample.0.weight"], None, stride, 0)
-        residual = _bn(residual, sd, prefix + ".downsample.1", eps, momentum, training, stats)
-    return F.relu(out + residual)
+        residual = q(F.conv2d(x, qw(sd[prefix + ".downsample.0.weight"]), None, stride, 0))
+        residual = q(_bn(residual, sd, prefix + ".downsample.1", eps, momentum, training, stats))
+    return q(F.relu(out + residual))
 
 
 def resnet18(x, sd, prefix, eps, momentum, training, stats=None):
     """ResNet.forward (deep_stem=False, BasicBlock [2,2,2,2]) — resnet.py:126-184"""
-    x = F.conv2d(x, sd[prefix + ".conv1.weight"], None, 2, 3)
-    x = F.relu(_bn(x, sd, prefix + ".bn1", eps, momentum, training, stats))
+    x = q(F.conv2d(q(x), qw(sd[prefix + ".conv1.weight"]), None, 2, 3))
+    x = q(F.relu(_bn(x, sd, prefix + ".bn1", eps, momentum, training, stats)))
     x = F.max_pool2d(x, 3, 2, 1)
     blocks = []
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
@@ -114,47 +145,47 @@ def resnet18(x, sd, prefix, eps, momentum, training, stats=None):
 def attention_refinement(x, sd, prefix, eps, momentum, training, stats=None):
     """AttentionRefinement.forward — seg_oprs.py:207-212"""
     fm = conv_bn_relu(x, sd, prefix + ".conv_3x3", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
-    se = F.adaptive_avg_pool2d(fm, 1)
+    se = q(F.adaptive_avg_pool2d(fm, 1))
     se = conv_bn_relu(se, sd, prefix + ".channel_attention.1", 1, 0, has_relu=False, eps=eps, momentum=momentum,
                       training=training, stats=stats)
-    return fm * torch.sigmoid(se)
+    return fm * torch.sigmoid(se)  # rounded by the caller after `+ last_fm` (one fused kernel on the B200 path)
 
 
 def feature_fusion(x1, x2, sd, prefix, eps, momentum, training, stats=None):
     """FeatureFusion.forward — seg_oprs.py:233-238"""
     fm = torch.cat([x1, x2], dim=1)
     fm = conv_bn_relu(fm, sd, prefix + ".conv_1x1", 1, 0, eps=eps, momentum=momentum, training=training, stats=stats)
-    se = F.adaptive_avg_pool2d(fm, 1)
+    se = q(F.adaptive_avg_pool2d(fm, 1))
     se = conv_bn_relu(se, sd, prefix + ".channel_attention.1", 1, 0, has_bn=False, has_relu=True)
     se = conv_bn_relu(se, sd, prefix + ".channel_attention.2", 1, 0, has_bn=False, has_relu=False)
-    return fm + fm * torch.sigmoid(se)
+    return q(fm + fm * torch.sigmoid(se))
 
 
 def bisenet_head_logits(x, sd, prefix, eps, momentum, training, stats=None):
     """BiSeNetHead.forward up to the low-resolution logits — bisenet network.py:162-163"""
     fm = conv_bn_relu(x, sd, prefix + ".conv_3x3", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
-    return F.conv2d(fm, sd[prefix + ".conv_1x1.weight"], sd[prefix + ".conv_1x1.bias"])
+    return F.conv2d(fm, qw(sd[prefix + ".conv_1x1.weight"]), sd[prefix + ".conv_1x1.bias"])  # fp32 logits
 
 
 def bisenet_r18_forward(data, sd, eps=1e-5, momentum=0.1, training=True, stats=None):
     """BiSeNet.forward wiring — /root/reference/model/bisenet/cityscapes.bisenet.R18/network.py:75-111.
     Returns the three LOW-resolution logit tensors (aux0 @1/16 scale 16, aux1 @1/8, main @1/8) and features."""
     kw = dict(eps=eps, momentum=momentum, training=training, stats=stats)
-    sp = conv_bn_relu(data, sd, "spatial_path.conv_7x7", 2, 3, **kw)
+    sp = conv_bn_relu(q(data), sd, "spatial_path.conv_7x7", 2, 3, **kw)
     sp = conv_bn_relu(sp, sd, "spatial_path.conv_3x3_1", 2, 1, **kw)
     sp = conv_bn_relu(sp, sd, "spatial_path.conv_3x3_2", 2, 1, **kw)
     sp = conv_bn_relu(sp, sd, "spatial_path.conv_1x1", 1, 0, **kw)
     blocks = resnet18(data, sd, "context_path", eps, momentum, training, stats)
     blocks = blocks[::-1]
-    gc = F.adaptive_avg_pool2d(blocks[0], 1)
+    gc = q(F.adaptive_avg_pool2d(blocks[0], 1))
     gc = conv_bn_relu(gc, sd, "global_context.1", 1, 0, **kw)
-    gc = F.interpolate(gc, size=blocks[0].shape[2:], mode="bilinear", align_corners=True)
+    gc = q(F.interpolate(gc, size=blocks[0].shape[2:], mode="bilinear", align_corners=True))
     last = gc
     pred_out = []
     for i in range(2):
         fm = attention_refinement(blocks[i], sd, "arms.%d" % i, eps, momentum, training, stats)
-        fm = fm + last
-        last = F.interpolate(fm, size=blocks[i + 1].shape[2:], mode="bilinear", align_corners=True)
+        fm = q(fm + last)
+        last = q(F.interpolate(fm, size=blocks[i + 1].shape[2:], mode="bilinear", align_corners=True))
         last = conv_bn_relu(last, sd, "refines.%d" % i, 1, 1, **kw)
         pred_out.append(last)
     ffm = feature_fusion(sp, last, sd, "ffm", eps, momentum, training, stats)

@@ -143,9 +143,10 @@ def test_conv_full_size_linearity(cuda):
     b = torch.randint(-4, 5, (N, H, W, C), device=cuda, generator=g).to(torch.bfloat16).permute(0, 3, 1, 2)
     w = (torch.randint(-2, 3, (K, 3, 3, C), device=cuda, generator=g).float() / 4)
     wb = w.to(torch.bfloat16)
-    ya = ops.conv_fprop(a, wb, K, 3, 1, 1, 1).float()
-    yb = ops.conv_fprop(b, wb, K, 3, 1, 1, 1).float()
-    yab = ops.conv_fprop((a + b), wb, K, 3, 1, 1, 1).float()
-    assert torch.equal(ya + yb, yab)  # all partial sums are small integers / 4: exact in fp32 and bf16
+    f32 = torch.float32
+    ya = ops.conv_fprop(a, wb, K, 3, 1, 1, 1, out_dtype=f32)
+    yb = ops.conv_fprop(b, wb, K, 3, 1, 1, 1, out_dtype=f32)
+    yab = ops.conv_fprop((a + b), wb, K, 3, 1, 1, 1, out_dtype=f32)
+    assert torch.equal(ya + yb, yab)  # all partial sums are small integers / 4: exact in fp32
     ref = F.conv2d(a[:2].float(), w.permute(0, 3, 1, 2), None, 1, 1)
     assert torch.equal(ya[:2], ref)

@@ -133,7 +133,7 @@ def test_ohem_full_size_properties(cuda):
     _, _, p, state, _ = loss.grad_fn.saved_tensors
     st = ops.ohem_state_dict(state)
     assert st["num_valid"] == int((labels != 255).sum())
-    assert st["active"] and st["T"] >= 0.7
+    assert st["active"] and np.float32(st["T"]) >= np.float32(0.7)
     kept = int(((labels.reshape(-1) != 255) & (p <= st["T"])).sum())
     assert kept == st["kept"]
     n_le = int((p <= st["T"]).sum())

@@ -11,6 +11,7 @@ from . import _lib
 from ._lib import BF16, F32, ConvShape, call, ptr, stream
 
 import ctypes
+import weakref
 
 _BF = torch.bfloat16
 
@@ -32,14 +33,21 @@ def nhwc_zeros(N, C, H, W, dtype=_BF, device="cuda", cs=None):
 
 
 def cs_of(t):
-    """channel stride of an NHWC-backed logical NCHW tensor; validates the layout"""
+    """channel stride (elements between consecutive pixels) of an NHWC-backed logical NCHW tensor"""
     assert t.dim() == 4, "expected a 4-D tensor"
     N, C, H, W = t.shape
     s = t.stride()
     if C > 1 and s[1] != 1:
         raise ValueError("tensor is not NHWC-backed (channel stride %d); use to_nhwc()" % s[1])
-    cs = s[3]
-    if (W > 1 and s[2] != W * cs) or (H * W > 1 and N > 1 and s[0] != H * W * cs):
+    if W > 1:
+        cs = s[3]
+    elif H > 1:
+        cs = s[2]
+    elif N > 1:
+        cs = s[0]
+    else:
+        cs = C
+    if (W > 1 and H > 1 and s[2] != W * cs) or (H * W > 1 and N > 1 and s[0] != H * W * cs) or cs < C:
         raise ValueError("tensor is not a dense NHWC buffer: shape %s strides %s" % (tuple(t.shape), s))
     return cs
 
@@ -83,15 +91,15 @@ class _PackCache:
         self.cache.clear()
 
     def get(self, w, want_t, pad_k=None, stem=False):
-        key = (w.data_ptr(), bool(want_t), pad_k, stem, w._version)
+        key = (id(w), w.data_ptr(), bool(want_t), pad_k, stem, w._version)
         hit = self.cache.get(key)
-        if hit is not None:
-            return hit
+        if hit is not None and hit[2]() is w:
+            return hit[0], hit[1]
         K, C, R, S = w.shape
         if stem:
             wp = torch.empty((K, 4, 4, 16), dtype=_BF, device=w.device)
             call("tsb_pack_stem_weight", ptr(_krsc_ptr(w)), K, ptr(wp), stream())
-            out = (wp, None)
+            out = (wp, None, weakref.ref(w))
         else:
             src = _krsc_ptr(w)
             if pad_k is not None and pad_k != K:  # classifier: pad K (19) up to 64 rows of zeros
@@ -101,9 +109,9 @@ class _PackCache:
             wb = torch.empty((K, R, S, C), dtype=_BF, device=w.device)
             wt = torch.empty((C, R, S, K), dtype=_BF, device=w.device) if want_t else None
             call("tsb_pack_weight", ptr(src), K, R, S, C, ptr(wb), ptr(wt), stream())
-            out = (wb, wt)
+            out = (wb, wt, weakref.ref(w))
         self.cache[key] = out
-        return out
+        return out[0], out[1]
 
 
 pack_cache = _PackCache()
@@ -123,6 +131,47 @@ def _allreduce_stats(buf):
 
 
 # --------------------------------------------------------------------------------------------------
+# optional CUDA-event bracketing of the conv launches (bench.py roofline: algorithmic FLOPs / kernel time)
+# --------------------------------------------------------------------------------------------------
+class _ConvProf(object):
+    def __init__(self):
+        self.on = False
+        self.recs = []
+
+    def enable(self):
+        self.on, self.recs = True, []
+
+    def disable(self):
+        self.on = False
+
+    def begin(self):
+        if not self.on:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, e0, flops):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.recs.append((e0, e1, flops))
+
+    def collect(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.recs)
+        return dict(ms=ms, flops=float(sum(f for _, _, f in self.recs)), launches=len(self.recs))
+
+
+conv_prof = _ConvProf()
+
+
+def _conv_flops(shp):
+    return 2.0 * shp.N * shp.P * shp.Q * shp.K * shp.C * shp.R * shp.S
+
+
+# --------------------------------------------------------------------------------------------------
 # low-level conv calls
 # --------------------------------------------------------------------------------------------------
 def conv_fprop(x, wb, K, R, stride, pad, dil, bias=None, out_dtype=_BF, out=None, ocs=None, stats=None):
@@ -134,8 +183,10 @@ def conv_fprop(x, wb, K, R, stride, pad, dil, bias=None, out_dtype=_BF, out=None
     s1 = s2 = None
     if stats is not None:
         s1, s2 = stats[0], stats[1]
+    ev = conv_prof.begin()
     call("tsb_conv2d_fprop", ctypes.byref(shp), ptr(x), cs_of(x), ptr(wb), ptr(bias), ptr(out), _lib.dt(out), cs_of(out),
          ptr(s1), ptr(s2), stream())
+    conv_prof.end(ev, _conv_flops(shp))
     return out
 
 
@@ -144,14 +195,18 @@ def conv_dgrad(dy, wt, xshape, K, R, stride, pad, dil, out=None, accumulate=Fals
     shp = make_shape(N, H, W, C, K, R, stride, pad, dil)
     if out is None:
         out = nhwc_empty(N, C, H, W, device=dy.device)
+    ev = conv_prof.begin()
     call("tsb_conv2d_dgrad", ctypes.byref(shp), ptr(dy), cs_of(dy), ptr(wt), ptr(out), cs_of(out), int(accumulate), stream())
+    conv_prof.end(ev, _conv_flops(shp))
     return out
 
 
 def conv_wgrad(x, dy, K, R, stride, pad, dil, dw_krsc):
     N, C, H, W = x.shape
     shp = make_shape(N, H, W, C, K, R, stride, pad, dil)
+    ev = conv_prof.begin()
     call("tsb_conv2d_wgrad", ctypes.byref(shp), ptr(x), cs_of(x), ptr(dy), cs_of(dy), ptr(dw_krsc), stream())
+    conv_prof.end(ev, _conv_flops(shp))
 
 
 def _new_wgrad(w):
@@ -194,8 +249,10 @@ class ConvBNActFn(torch.autograd.Function):
         raw = nhwc_empty(N, K, P, Q, device=dev)
         if stem:
             wp, _ = pack_cache.get(w, False, stem=True)
+            ev = conv_prof.begin()
             call("tsb_conv_stem_fprop", ptr(x), N, H, W, ptr(wp), K, ptr(raw), K, ptr(stats[0]) if training else None,
                  ptr(stats[1]) if training else None, stream())
+            conv_prof.end(ev, 2.0 * N * P * Q * K * 147)
         else:
             wb, _ = pack_cache.get(w, False)
             conv_fprop(x, wb, K, R, stride, pad, dil, out=raw, stats=stats)
@@ -245,7 +302,9 @@ class ConvBNActFn(torch.autograd.Function):
         if stem:
             H, W = P * 2, Q * 2
             dwp = torch.zeros((K, 4, 64), dtype=torch.float32, device=dev)
+            ev = conv_prof.begin()
             call("tsb_conv_stem_wgrad", ptr(x), N, H, W, ptr(draw), K, K, ptr(dwp), stream())
+            conv_prof.end(ev, 2.0 * N * P * Q * K * 147)
             call("tsb_unpack_stem_wgrad", ptr(dwp), K, ptr(dw), stream())
         else:
             conv_wgrad(x, draw, K, R, stride, pad, dil, dw)

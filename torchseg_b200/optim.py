@@ -27,10 +27,10 @@ class SGD(object):
         self.flat_param, self._spans = flatten(self._params, "data")
         self.flat_grad, _ = ensure_flat_grads(self._params)
         self.flat_mom = torch.zeros_like(self.flat_param)
-        ends, off = [], 0
+        ends, idx = [], 0
         for g in self.param_groups:
-            off += sum(p.numel() for p in g["params"])
-            ends.append(off)
+            idx += len(g["params"])
+            ends.append(self._spans[idx - 1][1] if idx > 0 else 0)
         dev = self.flat_param.device
         self._seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
         self._steps = 0
