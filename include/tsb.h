@@ -124,11 +124,12 @@ int tsb_adaptive_avgpool_fwd(const void* in, int ics, int N, int C, int H, int W
 /* din(bf16) (+)= dout[n, bin(h), bin(w), c] / bin_area  (S==1 → broadcast of dout/(H*W)) */
 int tsb_adaptive_avgpool_bwd(const float* dout, int N, int C, int H, int W, int S, void* din, int ics,
                              int accumulate, tsb_stream_t stream);
-int tsb_maxpool3x3s2_fwd(const void* in, int ics, void* out, int ocs, int N, int C, int H, int W,
+/* argmax (optional): uint8 [N,P,Q,C] window position r*3+s of the FIRST maximum in scan order (ATen
+ * max_pool2d tie semantics); the backward is a gather over it. */
+int tsb_maxpool3x3s2_fwd(const void* in, int ics, void* out, int ocs, void* argmax, int N, int C, int H, int W,
                          tsb_stream_t stream);
-/* gather-form backward: recomputes the arg-max (first maximum in scan order, like ATen) from `in` */
-int tsb_maxpool3x3s2_bwd(const void* in, int ics, const void* dout, int ocs, void* din, int dcs, int N, int C,
-                         int H, int W, tsb_stream_t stream);
+int tsb_maxpool3x3s2_bwd(const void* argmax, const void* dout, int ocs, void* din, int dcs, int N, int C, int H,
+                         int W, tsb_stream_t stream);
 
 /* ================================================================================================
  * BatchNorm (training) — replaces norm_layer(...) inside ConvBnRelu (seg_oprs.py:34,42), resnet

@@ -40,8 +40,8 @@ _SIGS = {
     "tsb_bilinear_fwd_nhwc_to_nchw": [P, I, I, P, I, I, I, I, I, I, P],
     "tsb_adaptive_avgpool_fwd": [P, I, I, I, I, I, I, P, P],
     "tsb_adaptive_avgpool_bwd": [P, I, I, I, I, I, P, I, I, P],
-    "tsb_maxpool3x3s2_fwd": [P, I, P, I, I, I, I, I, P],
-    "tsb_maxpool3x3s2_bwd": [P, I, P, I, P, I, I, I, I, I, P],
+    "tsb_maxpool3x3s2_fwd": [P, I, P, I, P, I, I, I, I, P],
+    "tsb_maxpool3x3s2_bwd": [P, P, I, P, I, I, I, I, I, P],
     "tsb_bn_stats": [P, I, L, I, P, P, P],
     "tsb_bn_finalize": [P, P, D, I, P, P, F, F, P, P, P, P, P, P, P],
     "tsb_bn_apply": [P, I, P, P, P, I, I, P, I, L, I, P],

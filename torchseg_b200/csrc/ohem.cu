@@ -164,36 +164,68 @@ ohem_ptarget_kernel_anyc(const T* __restrict__ logits, long long sn, long long s
     pt_flush(s_hist, acc, state, s_red);
 }
 
-// fused bilinear-upsample variant: low-res fp32 NHWC logits [N,h,w,cs]
+// ---------------------------------------------------------------------------------------------
+// Fused bilinear-upsample kernels work on BANDS: CTA = (x-strip of kStrip hi-res columns, low-res row i,
+// image n). All hi-res rows y with floor(ry*y) == i share the two low-res source rows (i, i1), which are
+// staged once in shared memory together with the per-column lerp coefficients.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStrip = 256;          // hi-res columns per CTA (== kThreads)
+// low-res columns a strip can touch: kStrip*w/W + 3; the two staged source rows live in DYNAMIC shared memory
+// sized by the host from the actual scale (s_lo[2][maxcols][CMAX])
+
+struct BandGeom {
+    int y_lo, y_hi;   // candidate hi-res rows (membership re-checked exactly)
+    int jbase, ncols; // low-res columns [jbase, jbase+ncols) touched by this strip
+};
+__device__ __forceinline__ BandGeom band_geom(float ry, float rx, int ci, int x0, int x1 /*exclusive*/, int H, int w) {
+    BandGeom g;
+    if (ry > 0.f) {
+        g.y_lo = max(0, (int)floorf((float)ci / ry) - 1);
+        g.y_hi = min(H - 1, (int)ceilf((float)(ci + 1) / ry) + 1);
+    } else { g.y_lo = 0; g.y_hi = H - 1; }
+    Lerp a = make_lerp(rx, x0, w), b = make_lerp(rx, x1 - 1, w);
+    g.jbase = a.i0;
+    g.ncols = b.i1 - a.i0 + 1;
+    return g;
+}
+
 template <int CMAX>
 __global__ void __launch_bounds__(kThreads)
 ohem_ptarget_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64_t* __restrict__ labels, int N,
                        int C, int H, int W, int ignore_label, float thresh, float* __restrict__ p,
-                       float* __restrict__ nll, uint32_t* state) {
+                       float* __restrict__ nll, uint32_t* state, int maxcols) {
     __shared__ unsigned int s_hist[4096];
     __shared__ float s_red[33];
+    extern __shared__ float s_lo_dyn[];  // [2][maxcols][CMAX]: the two low-res source rows of this band
     for (int b = threadIdx.x; b < 4096; b += kThreads) s_hist[b] = 0;
-    __syncthreads();
     PtAccum acc;
     const float ry = area_scale(h, H), rx = area_scale(w, W);
-    const long long total = (long long)N * H * W;
-    const long long hw = (long long)H * W;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int n = (int)(i / hw);
-        long long r = i - (long long)n * hw;
-        int y = (int)(r / W), x = (int)(r - (long long)y * W);
+    const int n = blockIdx.z, ci = blockIdx.y, x0 = blockIdx.x * kStrip, x1 = min(W, x0 + kStrip);
+    const int i1 = ci + (ci < h - 1 ? 1 : 0);
+    const BandGeom g = band_geom(ry, rx, ci, x0, x1, H, w);
+    if (g.ncols > maxcols) __trap();
+    float* s_lo0 = s_lo_dyn;
+    float* s_lo1 = s_lo_dyn + maxcols * CMAX;
+    for (int q = threadIdx.x; q < 2 * g.ncols * C; q += kThreads) {
+        int c = q % C, t2 = q / C, col = t2 % g.ncols, row = t2 / g.ncols;
+        (row ? s_lo1 : s_lo0)[col * CMAX + c] = __ldg(lo + (((long long)n * h + (row ? i1 : ci)) * w + g.jbase + col) * cs + c);
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    const bool xin = x < x1;
+    const Lerp lx = make_lerp(rx, xin ? x : x0, w);
+    const int j0 = lx.i0 - g.jbase, j1 = lx.i1 - g.jbase;
+    for (int y = g.y_lo; y <= g.y_hi; ++y) {
+        const Lerp ly = make_lerp(ry, y, h);
+        if (ly.i0 != ci || !xin) continue;  // uniform in y across the CTA
+        const long long i = ((long long)n * H + y) * W + x;
         long long lab = labels[i];
         bool valid = lab != (long long)ignore_label;
         int t = valid ? (int)lab : 0;
-        Lerp ly = make_lerp(ry, y, h), lx = make_lerp(rx, x, w);
-        const float* b00 = lo + (((long long)n * h + ly.i0) * w + lx.i0) * cs;
-        const float* b01 = lo + (((long long)n * h + ly.i0) * w + lx.i1) * cs;
-        const float* b10 = lo + (((long long)n * h + ly.i1) * w + lx.i0) * cs;
-        const float* b11 = lo + (((long long)n * h + ly.i1) * w + lx.i1) * cs;
         float v[CMAX];
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-            if (c < C) v[c] = lerp4(ly, lx, __ldg(b00 + c), __ldg(b01 + c), __ldg(b10 + c), __ldg(b11 + c));
+            if (c < C) v[c] = lerp4(ly, lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c], s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
         float p_t, nl;
         softmax_target<CMAX>(v, C, t, p_t, nl);
         pt_emit(i, valid, p_t, nl, thresh, p, nll, s_hist, acc);
@@ -401,103 +433,121 @@ ohem_grad_kernel(const T* __restrict__ logits, long long sn, long long sc, long 
 }
 
 // ---------------------------------------------------------------------------------------------
-// gradient, fused-upsample form.  One warp per low-res cell (n,i,j): the hi-res pixels whose bilinear
-// stencil has (i,j) as top-left corner contribute only to the cell's 4 corners, so the warp keeps
-// 4 x C register accumulators, shuffle-reduces them and issues 4*C red.global.add.f32.
+// gradient, fused-upsample form (band structure as above).  Per hi-res row of the band:
+//   phase 1: thread x computes g[c] = (softmax_c - onehot_c) * w_t * scale for its pixel → smem s_g[c][x]
+//   phase 2: thread (j,c) forms s = Σ_x wx(x,j) g[c][x] over the <= ~2*scale columns that touch low-res
+//            column j and accumulates top += l0(y)*s, bot += l1(y)*s in registers.
+// After the band: red.global.add of top → row i, bot → row i1.  No shuffles, no per-pixel atomics.
 // ---------------------------------------------------------------------------------------------
 template <int CMAX>
 __global__ void __launch_bounds__(kThreads)
 ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64_t* __restrict__ labels,
                     const float* __restrict__ p, int N, int C, int H, int W, int ignore_label,
                     const float* __restrict__ cw, const uint32_t* __restrict__ state,
-                    const float* __restrict__ gscale, float* __restrict__ dlo) {
-    __shared__ float s_corner[kThreads / 32][4][CMAX];
-    __shared__ float s_out[kThreads / 32][4][CMAX];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+                    const float* __restrict__ gscale, float* __restrict__ dlo, int maxcols) {
+    constexpr int kPitch = kStrip + 1;  // odd pitch → conflict-free column walks in phase 2
+    extern __shared__ float s_dyn[];    // s_g[CMAX][kPitch] then s_lo[2][maxcols][CMAX]
+    float (*s_g)[kPitch] = reinterpret_cast<float (*)[kPitch]>(s_dyn);
+    float* s_lo0 = s_dyn + CMAX * kPitch;
+    float* s_lo1 = s_lo0 + maxcols * CMAX;
+    __shared__ float s_l0[kStrip], s_l1[kStrip];
+    __shared__ short s_j0[kStrip], s_j1[kStrip];
     const bool active = state[ST_ACTIVE] != 0;
     const float Tth = __uint_as_float(state[ST_THRESH]);
     const float scale = __uint_as_float(state[ST_INVDEN]) * (gscale ? *gscale : 1.f);
     const float ry = area_scale(h, H), rx = area_scale(w, W);
-    const long long ncells = (long long)N * h * w;
-    for (long long cell = (long long)blockIdx.x * (kThreads / 32) + wib; cell < ncells;
-         cell += (long long)gridDim.x * (kThreads / 32)) {
-        int n = (int)(cell / ((long long)h * w));
-        int rem = (int)(cell - (long long)n * h * w);
-        int ci = rem / w, cj = rem - ci * w;
-        int i1 = ci + (ci < h - 1 ? 1 : 0), j1 = cj + (cj < w - 1 ? 1 : 0);
-        const long long o00 = (((long long)n * h + ci) * w + cj) * cs, o01 = (((long long)n * h + ci) * w + j1) * cs;
-        const long long o10 = (((long long)n * h + i1) * w + cj) * cs, o11 = (((long long)n * h + i1) * w + j1) * cs;
-        __syncwarp();
-        if (lane < C) {
-            s_corner[wib][0][lane] = __ldg(lo + o00 + lane);
-            s_corner[wib][1][lane] = __ldg(lo + o01 + lane);
-            s_corner[wib][2][lane] = __ldg(lo + o10 + lane);
-            s_corner[wib][3][lane] = __ldg(lo + o11 + lane);
-        }
-        __syncwarp();
-        // candidate hi-res box (one pixel of slack each side; membership is re-checked exactly)
-        int y_lo, y_hi, x_lo, x_hi;
-        if (ry > 0.f) {
-            y_lo = max(0, (int)floorf((float)ci / ry) - 1);
-            y_hi = min(H - 1, (int)ceilf((float)(ci + 1) / ry) + 1);
-        } else { y_lo = 0; y_hi = H - 1; }
-        if (rx > 0.f) {
-            x_lo = max(0, (int)floorf((float)cj / rx) - 1);
-            x_hi = min(W - 1, (int)ceilf((float)(cj + 1) / rx) + 1);
-        } else { x_lo = 0; x_hi = W - 1; }
-        const int bw = x_hi - x_lo + 1, bh = y_hi - y_lo + 1;
-        float acc[4][CMAX];
+    const int n = blockIdx.z, ci = blockIdx.y, x0 = blockIdx.x * kStrip, x1 = min(W, x0 + kStrip);
+    const int i1 = ci + (ci < h - 1 ? 1 : 0);
+    const BandGeom g = band_geom(ry, rx, ci, x0, x1, H, w);
+    if (g.ncols > maxcols) __trap();
+    for (int q = threadIdx.x; q < 2 * g.ncols * C; q += kThreads) {
+        int c = q % C, t2 = q / C, col = t2 % g.ncols, row = t2 / g.ncols;
+        (row ? s_lo1 : s_lo0)[col * CMAX + c] = __ldg(lo + (((long long)n * h + (row ? i1 : ci)) * w + g.jbase + col) * cs + c);
+    }
+    const int x = x0 + threadIdx.x;
+    const bool xin = x < x1;
+    const Lerp lx = make_lerp(rx, xin ? x : x0, w);
+    const int j0 = lx.i0 - g.jbase, j1 = lx.i1 - g.jbase;
+    s_j0[threadIdx.x] = xin ? (short)j0 : (short)-1;
+    s_j1[threadIdx.x] = xin ? (short)j1 : (short)-1;
+    s_l0[threadIdx.x] = lx.l0;
+    s_l1[threadIdx.x] = lx.l1;
+    // phase-2 ownership: pair q = j*C + c, up to 3 pairs per thread (ncols*C <= 72*19 would need more → loop)
+    constexpr int kMaxPairs = 6;  // host guarantees maxcols * C <= kMaxPairs * kThreads
+    float top[kMaxPairs], bot[kMaxPairs];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) acc[k][c] = 0.f;
-        for (int q = lane; q < bw * bh; q += 32) {
-            int yy = y_lo + q / bw, xx = x_lo + q % bw;
-            Lerp ly = make_lerp(ry, yy, h), lx = make_lerp(rx, xx, w);
-            if (ly.i0 != ci || lx.i0 != cj) continue;
-            long long pi = ((long long)n * H + yy) * W + xx;
+    for (int k = 0; k < kMaxPairs; ++k) { top[k] = 0.f; bot[k] = 0.f; }
+    const int npairs = g.ncols * C;
+    __syncthreads();
+    for (int y = g.y_lo; y <= g.y_hi; ++y) {
+        const Lerp ly = make_lerp(ry, y, h);
+        if (ly.i0 != ci) continue;  // uniform across the CTA
+        // ---- phase 1
+        bool kept = false;
+        int t = 0;
+        float wt = 0.f;
+        if (xin) {
+            const long long pi = ((long long)n * H + y) * W + x;
             long long lab = labels[pi];
-            bool kept = (lab != (long long)ignore_label) && (!active || p[pi] <= Tth);
-            if (!kept) continue;
-            int t = (int)lab;
-            float wt = (cw ? __ldg(cw + t) : 1.f) * scale;
+            kept = (lab != (long long)ignore_label) && (!active || p[pi] <= Tth);
+            t = kept ? (int)lab : 0;
+            if (kept) wt = (cw ? __ldg(cw + t) : 1.f) * scale;
+        }
+        if (kept) {
             float v[CMAX];
             float m = -INFINITY;
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
                 if (c < C) {
-                    v[c] = lerp4(ly, lx, s_corner[wib][0][c], s_corner[wib][1][c], s_corner[wib][2][c],
-                                 s_corner[wib][3][c]);
+                    v[c] = lerp4(ly, lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c], s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
                     m = fmaxf(m, v[c]);
                 }
-            float s = 0.f;
+            float ssum = 0.f;
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
-                if (c < C) { v[c] = __expf(v[c] - m); s += v[c]; }
-            float inv = wt / s;
-            const float w00 = ly.l0 * lx.l0, w01 = ly.l0 * lx.l1, w10 = ly.l1 * lx.l0, w11 = ly.l1 * lx.l1;
+                if (c < C) { v[c] = __expf(v[c] - m); ssum += v[c]; }
+            const float inv = wt / ssum;
 #pragma unroll
             for (int c = 0; c < CMAX; ++c)
-                if (c < C) {
-                    float g = v[c] * inv - (c == t ? wt : 0.f);
-                    acc[0][c] += w00 * g; acc[1][c] += w01 * g; acc[2][c] += w10 * g; acc[3][c] += w11 * g;
-                }
+                if (c < C) s_g[c][threadIdx.x] = v[c] * inv - (c == t ? wt : 0.f);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c)
+                if (c < C) s_g[c][threadIdx.x] = 0.f;
         }
+        __syncthreads();
+        // ---- phase 2
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C) {
-                    float r = warp_sum(acc[k][c]);
-                    if (lane == 0) s_out[wib][k][c] = r;
+        for (int k = 0; k < kMaxPairs; ++k) {
+            const int q = threadIdx.x + k * kThreads;
+            if (q < npairs) {
+                const int j = q / C, c = q - j * C;
+                // hi-res columns whose stencil touches low-res column jbase+j (one column of slack, exact re-check)
+                int xa, xb;
+                if (rx > 0.f) {
+                    xa = (int)floorf((float)(g.jbase + j - 1) / rx) - 1 - x0;
+                    xb = (int)ceilf((float)(g.jbase + j + 1) / rx) + 1 - x0;
+                } else { xa = 0; xb = kStrip - 1; }
+                xa = max(xa, 0);
+                xb = min(xb, x1 - x0 - 1);
+                float sacc = 0.f;
+                for (int xx = xa; xx <= xb; ++xx) {
+                    const float wgt = (s_j0[xx] == j ? s_l0[xx] : 0.f) + (s_j1[xx] == j ? s_l1[xx] : 0.f);
+                    sacc += wgt * s_g[c][xx];
                 }
-        __syncwarp();
-        if (lane < C) {
-            float a0 = s_out[wib][0][lane], a1 = s_out[wib][1][lane], a2 = s_out[wib][2][lane], a3 = s_out[wib][3][lane];
-            if (a0 != 0.f) atomicAdd(dlo + o00 + lane, a0);
-            if (a1 != 0.f) atomicAdd(dlo + o01 + lane, a1);
-            if (a2 != 0.f) atomicAdd(dlo + o10 + lane, a2);
-            if (a3 != 0.f) atomicAdd(dlo + o11 + lane, a3);
+                top[k] += ly.l0 * sacc;
+                bot[k] += ly.l1 * sacc;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPairs; ++k) {
+        const int q = threadIdx.x + k * kThreads;
+        if (q < npairs) {
+            const int j = q / C, c = q - j * C;
+            if (top[k] != 0.f) atomicAdd(dlo + (((long long)n * h + ci) * w + g.jbase + j) * cs + c, top[k]);
+            if (bot[k] != 0.f) atomicAdd(dlo + (((long long)n * h + i1) * w + g.jbase + j) * cs + c, bot[k]);
         }
     }
 }
@@ -537,15 +587,27 @@ extern "C" int tsb_ohem_ptarget(const void* logits, int dtype, long long sn, lon
     return TSB_OK;
 }
 
+namespace {
+// low-res columns one strip can touch
+inline int band_maxcols(int w, int W) { return (int)(((long long)kStrip * w + W - 1) / W) + 3; }
+}
+
 extern "C" int tsb_ohem_ptarget_up(const float* logits_lo, int cs, int h, int w, const int64_t* labels, int N, int C,
                                    int H, int W, int ignore_label, float thresh, float* p, float* nll, uint32_t* state,
                                    tsb_stream_t stream) {
     TSB_REQUIRE(logits_lo && labels && p && nll && state, "tsb_ohem_ptarget_up: null pointer");
     TSB_REQUIRE(N > 0 && C > 0 && C <= 32 && cs >= C && H > 0 && W > 0 && h > 0 && w > 0,
                 "tsb_ohem_ptarget_up: bad shape (C must be <= 32)");
-    long long total = (long long)N * H * W;
-    int grid = tsb_grid_for(total, kThreads, 8);
-    ohem_ptarget_up_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state);
+    TSB_REQUIRE(N <= 65535 && h <= 65535, "tsb_ohem_ptarget_up: N and h must fit a grid dimension");
+    const int maxcols = band_maxcols(w, W);
+    const int cmax = C <= 20 ? 20 : 32;
+    const size_t smem = sizeof(float) * 2 * (size_t)maxcols * cmax;
+    TSB_REQUIRE(smem <= 28 * 1024, "tsb_ohem_ptarget_up: up-scale factor W/w too small for the band kernel");
+    dim3 grid((W + kStrip - 1) / kStrip, h, N);
+    if (C <= 20)
+        ohem_ptarget_up_kernel<20><<<grid, kThreads, smem, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state, maxcols);
+    else
+        ohem_ptarget_up_kernel<32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state, maxcols);
     TSB_CUDA_CHECK_LAUNCH("ohem_ptarget_up");
     return TSB_OK;
 }
@@ -607,9 +669,23 @@ extern "C" int tsb_ohem_grad_up(const float* logits_lo, int cs, int h, int w, co
                                 const uint32_t* state, const float* gscale, float* dlogits_lo, tsb_stream_t stream) {
     TSB_REQUIRE(logits_lo && labels && p && state && dlogits_lo, "tsb_ohem_grad_up: null pointer");
     TSB_REQUIRE(C > 0 && C <= 32 && cs >= C, "tsb_ohem_grad_up: C must be <= 32");
-    long long ncells = (long long)N * h * w;
-    int grid = tsb_grid_for(ncells, kThreads / 32, 8);
-    ohem_grad_up_kernel<32><<<grid, kThreads, 0, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo);
+    TSB_REQUIRE(N <= 65535 && h <= 65535, "tsb_ohem_grad_up: N and h must fit a grid dimension");
+    const int maxcols = band_maxcols(w, W);
+    const int cmax = C <= 20 ? 20 : 32;
+    TSB_REQUIRE(maxcols * C <= 6 * kThreads, "tsb_ohem_grad_up: up-scale factor W/w too small for the band kernel");
+    const size_t smem = sizeof(float) * ((size_t)cmax * (kStrip + 1) + 2 * (size_t)maxcols * cmax);
+    TSB_REQUIRE(smem <= 96 * 1024, "tsb_ohem_grad_up: shared memory budget exceeded");
+    dim3 grid((W + kStrip - 1) / kStrip, h, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 20) {
+        static bool attr = false;
+        if (!attr) { TSB_CUDA_CALL(cudaFuncSetAttribute(ohem_grad_up_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+        ohem_grad_up_kernel<20><<<grid, kThreads, smem, st>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols);
+    } else {
+        static bool attr = false;
+        if (!attr) { TSB_CUDA_CALL(cudaFuncSetAttribute(ohem_grad_up_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+        ohem_grad_up_kernel<32><<<grid, kThreads, smem, st>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols);
+    }
     TSB_CUDA_CHECK_LAUNCH("ohem_grad_up");
     return TSB_OK;
 }

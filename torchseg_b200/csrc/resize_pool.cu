@@ -217,82 +217,75 @@ adaptive_avgpool_bwd_kernel(const float* __restrict__ dout, int N, int C8, int H
 }
 
 // ---------------------------------------------------------------- max pool 3x3 stride 2 pad 1
+// forward also records the arg-max window position r*3+s (first maximum in scan order, strict '>' — ATen
+// max_pool2d semantics) as one byte per output element, so the backward is a pure gather.
 __global__ void __launch_bounds__(kThreads)
-maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ics, __nv_bfloat16* __restrict__ out, int ocs, int N,
-                   int C8, int H, int W, int P, int Q) {
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ics, __nv_bfloat16* __restrict__ out, int ocs,
+                   uint8_t* __restrict__ idx, int N, int C8, int H, int W, int P, int Q) {
     const long long total = (long long)N * P * Q * C8;
-    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(idx % C8);
-        long long pix = idx / C8;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        int c8 = (int)(i % C8);
+        long long pix = i / C8;
         int q = (int)(pix % Q);
         long long t = pix / Q;
         int p = (int)(t % P), n = (int)(t / P);
         float m[8];
+        uint32_t am[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+        for (int k = 0; k < 8; ++k) { m[k] = -INFINITY; am[k] = 0; }
+#pragma unroll
         for (int r = 0; r < 3; ++r) {
             int h = 2 * p - 1 + r;
             if (h < 0 || h >= H) continue;
+#pragma unroll
             for (int s = 0; s < 3; ++s) {
                 int w = 2 * q - 1 + s;
                 if (w < 0 || w >= W) continue;
                 float v[8];
                 Vec8<__nv_bfloat16>::load(in + (((long long)n * H + h) * W + w) * ics + c8 * 8, v);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+                for (int k = 0; k < 8; ++k)
+                    if (v[k] > m[k]) { m[k] = v[k]; am[k] = r * 3 + s; }
             }
         }
         Vec8<__nv_bfloat16>::store(out + pix * ocs + c8 * 8, m);
+        if (idx) {
+            uint2 pk;
+            pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+            pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+            *reinterpret_cast<uint2*>(idx + pix * (long long)(C8 * 8) + c8 * 8) = pk;
+        }
     }
 }
 
-// backward, gather form: input pixel (h,w) receives dout[p,q] iff it is the FIRST maximum (scan order
-// r then s, strict '>' — ATen max_pool2d semantics) of window (p,q).
+// backward, gather form: input pixel (h,w) belongs to <= 4 windows; it receives dout[p,q] iff idx[p,q] names it.
 __global__ void __launch_bounds__(kThreads)
-maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ in, int ics, const __nv_bfloat16* __restrict__ dout, int ocs,
+maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dout, int ocs,
                    __nv_bfloat16* __restrict__ din, int dcs, int N, int C8, int H, int W, int P, int Q) {
     const long long total = (long long)N * H * W * C8;
-    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(idx % C8);
-        long long pix = idx / C8;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        int c8 = (int)(i % C8);
+        long long pix = i / C8;
         int w = (int)(pix % W);
         long long t = pix / W;
         int h = (int)(t % H), n = (int)(t / H);
-        const __nv_bfloat16* ib = in + (long long)n * H * W * ics + c8 * 8;
-        float me[8], acc[8];
-        Vec8<__nv_bfloat16>::load(ib + ((long long)h * W + w) * ics, me);
+        float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        for (int p = (h) / 2; p <= (h + 1) / 2; ++p) {     // windows with 2p-1 <= h <= 2p+1
-            if (p < 0 || p >= P) continue;
-            for (int q = (w) / 2; q <= (w + 1) / 2; ++q) {
-                if (q < 0 || q >= Q) continue;
-                // is (h,w) the first maximum of window (p,q)?
-                bool first[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) first[k] = true;
-                const int my_r = h - (2 * p - 1), my_s = w - (2 * q - 1);
-                for (int r = 0; r < 3; ++r) {
-                    int hh = 2 * p - 1 + r;
-                    if (hh < 0 || hh >= H) continue;
-                    for (int s = 0; s < 3; ++s) {
-                        int ww = 2 * q - 1 + s;
-                        if (ww < 0 || ww >= W) continue;
-                        if (r == my_r && s == my_s) continue;
-                        float v[8];
-                        Vec8<__nv_bfloat16>::load(ib + ((long long)hh * W + ww) * ics, v);
-                        bool before = (r < my_r) || (r == my_r && s < my_s);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            // an earlier element wins ties; a later one must be strictly greater
-                            if (before ? (v[k] >= me[k]) : (v[k] > me[k])) first[k] = false;
-                        }
-                    }
-                }
+        for (int p = h / 2; p <= (h + 1) / 2; ++p) {  // windows with 2p-1 <= h <= 2p+1
+            if (p >= P) continue;
+            for (int q = w / 2; q <= (w + 1) / 2; ++q) {
+                if (q >= Q) continue;
+                const uint32_t code = (uint32_t)((h - (2 * p - 1)) * 3 + (w - (2 * q - 1)));
+                const long long opix = ((long long)n * P + p) * Q + q;
+                uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + opix * (long long)(C8 * 8) + c8 * 8));
                 float g[8];
-                Vec8<__nv_bfloat16>::load(dout + (((long long)n * P + p) * Q + q) * ocs + c8 * 8, g);
+                Vec8<__nv_bfloat16>::load(dout + opix * ocs + c8 * 8, g);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += first[k] ? g[k] : 0.f;
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t a = ((k < 4 ? pk.x : pk.y) >> ((k & 3) * 8)) & 0xffu;
+                    acc[k] += (a == code) ? g[k] : 0.f;
+                }
             }
         }
         Vec8<__nv_bfloat16>::store(din + pix * dcs + c8 * 8, acc);
@@ -401,24 +394,24 @@ extern "C" int tsb_adaptive_avgpool_bwd(const float* dout, int N, int C, int H, 
     return TSB_OK;
 }
 
-extern "C" int tsb_maxpool3x3s2_fwd(const void* in, int ics, void* out, int ocs, int N, int C, int H, int W,
-                                    tsb_stream_t stream) {
+extern "C" int tsb_maxpool3x3s2_fwd(const void* in, int ics, void* out, int ocs, void* argmax, int N, int C, int H,
+                                    int W, tsb_stream_t stream) {
     TSB_REQUIRE(in && out && C % 8 == 0 && ics % 8 == 0 && ocs % 8 == 0, "tsb_maxpool3x3s2_fwd: bad args");
     const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
     long long total = (long long)N * P * Q * (C / 8);
     int grid = tsb_grid_for(total, kThreads, 8);
-    maxpool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ics, (__nv_bfloat16*)out, ocs, N, C / 8, H, W, P, Q);
+    maxpool_fwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ics, (__nv_bfloat16*)out, ocs, (uint8_t*)argmax, N, C / 8, H, W, P, Q);
     TSB_CUDA_CHECK_LAUNCH("maxpool_fwd");
     return TSB_OK;
 }
 
-extern "C" int tsb_maxpool3x3s2_bwd(const void* in, int ics, const void* dout, int ocs, void* din, int dcs, int N,
-                                    int C, int H, int W, tsb_stream_t stream) {
-    TSB_REQUIRE(in && dout && din && C % 8 == 0 && ics % 8 == 0 && ocs % 8 == 0 && dcs % 8 == 0, "tsb_maxpool3x3s2_bwd: bad args");
+extern "C" int tsb_maxpool3x3s2_bwd(const void* argmax, const void* dout, int ocs, void* din, int dcs, int N, int C,
+                                    int H, int W, tsb_stream_t stream) {
+    TSB_REQUIRE(argmax && dout && din && C % 8 == 0 && ocs % 8 == 0 && dcs % 8 == 0, "tsb_maxpool3x3s2_bwd: bad args");
     const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
     long long total = (long long)N * H * W * (C / 8);
     int grid = tsb_grid_for(total, kThreads, 8);
-    maxpool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, ics, (const __nv_bfloat16*)dout, ocs, (__nv_bfloat16*)din, dcs, N, C / 8, H, W, P, Q);
+    maxpool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const uint8_t*)argmax, (const __nv_bfloat16*)dout, ocs, (__nv_bfloat16*)din, dcs, N, C / 8, H, W, P, Q);
     TSB_CUDA_CHECK_LAUNCH("maxpool_bwd");
     return TSB_OK;
 }

@@ -368,18 +368,20 @@ class MaxPool3x3S2Fn(torch.autograd.Function):
         N, C, H, W = x.shape
         P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         y = nhwc_empty(N, C, P, Q, device=x.device)
-        call("tsb_maxpool3x3s2_fwd", ptr(x), cs_of(x), ptr(y), C, N, C, H, W, stream())
-        ctx.save_for_backward(x)
+        idx = torch.empty((N, P, Q, C), dtype=torch.uint8, device=x.device)
+        call("tsb_maxpool3x3s2_fwd", ptr(x), cs_of(x), ptr(y), C, ptr(idx), N, C, H, W, stream())
+        ctx.save_for_backward(idx)
+        ctx.shape = (N, C, H, W)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        N, C, H, W = x.shape
+        (idx,) = ctx.saved_tensors
+        N, C, H, W = ctx.shape
         if dy.dtype != _BF or dy.stride(1) != 1:
             dy = to_nhwc(dy)
-        dx = nhwc_empty(N, C, H, W, device=x.device)
-        call("tsb_maxpool3x3s2_bwd", ptr(x), cs_of(x), ptr(dy), cs_of(dy), ptr(dx), C, N, C, H, W, stream())
+        dx = nhwc_empty(N, C, H, W, device=dy.device)
+        call("tsb_maxpool3x3s2_bwd", ptr(idx), ptr(dy), cs_of(dy), ptr(dx), C, N, C, H, W, stream())
         return dx
 
 
