@@ -203,3 +203,26 @@ def bisenet_r18_loss(data, label, sd, min_kept, ignore_label=255, thresh=0.7, ep
         up = F.interpolate(l, scale_factor=s, mode="bilinear", align_corners=True)
         losses.append(ohem_ce(up, label, ignore_label, thresh, min_kept))
     return losses[2] + losses[0] + losses[1], lo
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs[0]: FCN-32s on a ResNet-18 backbone (plumbing case, CPU) — the reference ships FCN with
+# R101_v1c (/root/reference/model/fcn/voc.fcn32s.R101_v1c/network.py:13-68); the R18 variant keeps the same
+# head/loss wiring with resnet18(deep_stem=False) and heads _FCNHead(512,.) / _FCNHead(256,.).
+# Dropout2d(0.1) is disabled (p=0) so the case is deterministic.
+# --------------------------------------------------------------------------------------------------
+def fcn_head(x, sd, prefix, eps, momentum, training):
+    """_FCNHead.forward — fcn network.py:52-68: 3x3 CBR (C/4) → Dropout2d → 1x1 (+bias)"""
+    fm = conv_bn_relu(x, sd, prefix + ".cbr", 1, 1, eps=eps, momentum=momentum, training=training)
+    return F.conv2d(fm, sd[prefix + ".conv1x1.weight"], sd[prefix + ".conv1x1.bias"])
+
+
+def fcn_r18_loss(data, label, sd, aux_ratio=0.5, ignore_label=255, eps=1e-5, momentum=0.1):
+    """FCN.forward training branch — fcn network.py:33-47: bilinear x32 (aux x16), CE, loss + 0.5*aux"""
+    blocks = resnet18(data, sd, "backbone", eps, momentum, True)
+    fm = fcn_head(blocks[-1], sd, "head", eps, momentum, True)
+    pred = F.interpolate(fm, scale_factor=32, mode="bilinear", align_corners=True)
+    aux = fcn_head(blocks[-2], sd, "aux_head", eps, momentum, True)
+    aux = F.interpolate(aux, scale_factor=16, mode="bilinear", align_corners=True)
+    loss = F.cross_entropy(pred, label, ignore_index=ignore_label)
+    return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label)

@@ -1,0 +1,42 @@
+"""Seeded synthetic cases shared by tools/make_golden.py (live reference) and the parity tests."""
+import torch
+import torch.nn.functional as F
+
+OHEM_REGIMES = ["A", "B", "C", "D", "E"]
+
+
+def ohem_case(regime, N=2, C=19, H=48, W=64, seed=1234):
+    """SURVEY.md §8d regimes: A all kept (thr 0.7), B k-th value threshold, C min_kept > valid, D min_kept = 0,
+    E all ignored"""
+    g = torch.Generator().manual_seed(seed)
+    labels = torch.randint(0, C, (N, H, W), generator=g, dtype=torch.int64)
+    labels[:, : H // 10 + 1, :] = 255
+    logits = torch.randn(N, C, H, W, generator=g)
+    min_kept = N * H * W // 16
+    if regime == "B":
+        onehot = F.one_hot(labels.clamp(max=C - 1), C).permute(0, 3, 1, 2).float()
+        logits = 8 * onehot + logits
+    elif regime == "C":
+        min_kept = N * H * W
+    elif regime == "D":
+        min_kept = 0
+    elif regime == "E":
+        labels[:] = 255
+    return logits, labels, min_kept
+
+
+def bisenet_case(N=2, HW=128, seed=77):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, 3, HW, HW, generator=g)
+    y = torch.randint(0, 19, (N, HW, HW), generator=g, dtype=torch.int64)
+    y[:, : HW // 10, :] = 255
+    return x, y, N * HW * HW // 16, seed
+
+
+def fcn_case(N=2, HW=256, seed=304):
+    """BASELINE configs[0]: 2 synthetic 256x256 19-class images"""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, 3, HW, HW, generator=g)
+    y = torch.randint(0, 19, (N, HW, HW), generator=g, dtype=torch.int64)
+    y[:, : HW // 10, :] = 255
+    return x, y, seed

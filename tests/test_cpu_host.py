@@ -1,0 +1,187 @@
+"""CPU tests of the host-side mirror of the furnace API: Engine / State / checkpoints, LR policies, init_weight /
+group_weight, parse_devices, the FCN-R18 plumbing case (BASELINE configs[0]) and the world_size-2 gloo paths of
+the DDP / all_reduce_tensor replacements."""
+import argparse
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_poly_lr_matches_reference_formula():
+    from torchseg_b200.engine.lr_policy import PolyLR, MultiStageLR, LinearIncreaseLR
+    p = PolyLR(1e-2, 0.9, 80000)
+    assert p.get_lr(0) == 1e-2
+    assert abs(p.get_lr(40000) - 1e-2 * 0.5 ** 0.9) < 1e-12
+    assert MultiStageLR([(10, 0.1), (20, 0.01)]).get_lr(15) == 0.01
+    assert abs(LinearIncreaseLR(0.0, 1.0, 10).get_lr(5) - 0.5) < 1e-12
+
+
+def test_init_and_group_weight_semantics():
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.utils.init_func import init_weight, group_weight
+    m = BiSeNet(19, True, None, None, nn.BatchNorm2d)
+    init_weight(m.business_layer, nn.init.kaiming_normal_, nn.BatchNorm2d, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+    assert m.spatial_path.conv_7x7.bn.eps == 1e-5 and float(m.ffm.conv_1x1.bn.weight.min()) == 1.0
+    groups = group_weight([], m.context_path, nn.BatchNorm2d, 1e-2)
+    for mod in (m.spatial_path, m.global_context, m.arms, m.refines, m.heads, m.ffm):
+        groups = group_weight(groups, mod, nn.BatchNorm2d, 1e-1)
+    assert len(groups) == 14                      # train.py:70-84 → 7 x (decay, no-decay)
+    assert sum(len(g["params"]) for g in groups) == len(list(m.parameters()))
+    assert all(g.get("weight_decay", None) == 0.0 for g in groups[1::2])
+    # completeness assert fires for a module holding a bare Parameter (init_func.py:52-53)
+    class Bad(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = nn.Parameter(torch.zeros(3))
+    with pytest.raises(AssertionError):
+        group_weight([], Bad(), nn.BatchNorm2d, 0.1)
+
+
+def test_prepare_model_keeps_values_and_keys():
+    import torchseg_b200
+    from torchseg_b200.networks import BiSeNet
+    m = BiSeNet(19, True, None, None, nn.BatchNorm2d)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    ids = [id(p) for p in m.parameters()]
+    torchseg_b200.prepare_model(m)
+    assert ids == [id(p) for p in m.parameters()]
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k])
+    w = m.context_path.layer1[0].conv1.weight
+    assert w.permute(0, 2, 3, 1).is_contiguous()   # KRSC physical layout
+
+
+def test_parse_devices_and_engine_cli(monkeypatch, tmp_path):
+    from torchseg_b200.utils.pyt_utils import parse_devices
+    from torchseg_b200.engine.engine import Engine
+    assert parse_devices('') == [0] or len(parse_devices('')) >= 1
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    parser = argparse.ArgumentParser()
+    with Engine(custom_parser=parser, argv=[]) as engine:
+        assert engine.distributed is False and engine.world_size == 1
+        assert engine.continue_state_object is None
+        engine.update_iteration(3, 7)
+        assert engine.state.epoch == 3 and engine.state.iteration == 7
+        with pytest.raises(AssertionError):
+            engine.register_state(bogus=1)
+    with pytest.raises(SystemExit):   # -c must name an existing file (extant_file)
+        Engine(custom_parser=argparse.ArgumentParser(), argv=["-c", str(tmp_path / "missing.pth")])
+
+
+def test_fcn_r18_plumbing_cpu(tmp_path, monkeypatch):
+    """BASELINE configs[0]: FCN-32s R18, 2 x 256 x 256, CPU, 1 process — the train.py sequence (Engine, group_weight,
+    SGD, PolyLR, checkpoint save / link / restore) with the loss evaluated by the oracle restatement on the
+    module's own parameters (the B200 kernels do not run on a CPU)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_cases import fcn_case
+    from oracle import torch_ref
+    from torchseg_b200.engine.engine import Engine
+    from torchseg_b200.engine.lr_policy import PolyLR
+    from torchseg_b200.networks import FCN
+    from torchseg_b200.utils.init_func import init_weight, group_weight
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    x, y, seed = fcn_case()
+    with Engine(custom_parser=argparse.ArgumentParser(), argv=[]) as engine:
+        torch.manual_seed(seed)
+        model = FCN(19, backbone="R18")
+        init_weight(model.business_layer, nn.init.kaiming_normal_, nn.BatchNorm2d, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+        groups = group_weight([], model.backbone, nn.BatchNorm2d, 1e-2)
+        for m in model.business_layer:
+            groups = group_weight(groups, m, nn.BatchNorm2d, 1e-1)
+        opt = torch.optim.SGD(groups, lr=1e-2, momentum=0.9, weight_decay=1e-4)
+        lr_policy = PolyLR(1e-2, 0.9, 10)
+        engine.register_state(dataloader=None, model=model, optimizer=opt)
+        losses = []
+        for it in range(3):
+            opt.zero_grad()
+            engine.update_iteration(0, it)
+            sd = dict(model.named_parameters())
+            sd.update(dict(model.named_buffers()))
+            loss = torch_ref.fcn_r18_loss(x, y, sd)
+            lr = lr_policy.get_lr(it)
+            for i, g in enumerate(opt.param_groups):
+                g['lr'] = lr if i < 2 else lr * 10
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        assert losses[-1] < losses[0]
+        snap = tmp_path / "log" / "snapshot"
+        engine.save_and_link_checkpoint(str(snap), str(tmp_path / "log"), str(tmp_path / "log_link"))
+        ck = torch.load(str(snap / "epoch-0.pth"), weights_only=False)
+        assert set(ck.keys()) == {"model", "optimizer", "epoch", "iteration"}       # engine.py:95-105
+        assert not any(k.startswith("module.") for k in ck["model"])
+        assert os.path.islink(str(snap / "epoch-last.pth"))
+        # restore into a fresh model through -c
+        model2 = FCN(19, backbone="R18")
+        opt2 = torch.optim.SGD(group_weight([], model2, nn.BatchNorm2d, 1e-2), lr=1e-2, momentum=0.9)
+    with Engine(custom_parser=argparse.ArgumentParser(), argv=["-c", str(snap / "epoch-last.pth")]) as e2:
+        groups2 = group_weight([], model2.backbone, nn.BatchNorm2d, 1e-2)
+        for m in model2.business_layer:
+            groups2 = group_weight(groups2, m, nn.BatchNorm2d, 1e-1)
+        opt2 = torch.optim.SGD(groups2, lr=1e-2, momentum=0.9, weight_decay=1e-4)
+        e2.register_state(dataloader=None, model=model2, optimizer=opt2)
+        e2.restore_checkpoint()
+        assert e2.state.epoch == 1 and e2.state.iteration == 2                     # engine.py:144-145
+        for (k, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+            assert torch.equal(a, b), k
+
+
+# ------------------------------------------------------------------------------------------------- world_size 2
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from torchseg_b200.engine.engine import Engine
+    from torchseg_b200.utils.pyt_utils import all_reduce_tensor
+    from torchseg_b200.apex.parallel import DistributedDataParallel, SyncBatchNorm
+    try:
+        with Engine(custom_parser=argparse.ArgumentParser(), argv=[]) as engine:
+            assert engine.distributed and engine.world_size == world and engine.local_rank == rank
+            assert engine.devices == list(range(world))
+            t = all_reduce_tensor(torch.tensor([float(rank + 1)]), world_size=world)
+            assert abs(float(t) - sum(range(1, world + 1)) / world) < 1e-6           # pyt_utils.py:34-39
+            torch.manual_seed(rank)                                                   # ranks start different …
+            net = nn.Sequential(nn.Conv2d(3, 4, 3, padding=1, bias=False), SyncBatchNorm(4), nn.Conv2d(4, 2, 1))
+            ddp = DistributedDataParallel(net, bucket_bytes=64)                        # … the ctor broadcasts rank 0
+            w0 = [p.detach().clone() for p in net.parameters()]
+            gathered = [torch.zeros_like(w0[0]) for _ in range(world)]
+            dist.all_gather(gathered, w0[0])
+            assert all(torch.equal(g, gathered[0]) for g in gathered)
+            # per-rank gradients g_r = (rank+1) * ones → averaged to mean(rank+1)
+            ddp.zero_grad()
+            loss = sum(((rank + 1.0) * p).sum() for p in net.parameters())
+            loss.backward()
+            ddp.finish_reduce()
+            expect = sum(range(1, world + 1)) / world
+            for p in net.parameters():
+                assert torch.allclose(p.grad, torch.full_like(p.grad, expect)), (rank, p.grad.flatten()[:3])
+                # gradients are views into ONE flat buffer
+                lo = ddp.flat_grad.data_ptr()
+                assert lo <= p.grad.data_ptr() < lo + ddp.flat_grad.numel() * 4
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL: %s\n%s" % (e, traceback.format_exc())))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_ddp_and_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(r[1] == "ok" for r in res), res

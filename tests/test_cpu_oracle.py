@@ -1,0 +1,183 @@
+"""CPU tests: the oracle against the golden vectors generated from the LIVE reference (tools/make_golden.py),
+against the live reference itself when /root/reference is present, and the two oracle restatements (C and
+torch) against each other."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_cases import ohem_case, bisenet_case, fcn_case, OHEM_REGIMES
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_outputs.json")))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("regime", OHEM_REGIMES)
+def test_c_oracle_ohem_vs_golden(regime):
+    from oracle import c_oracle
+    logits, labels, min_kept = ohem_case(regime)
+    g = GOLD["ohem"][regime]
+    out = c_oracle.ohem(logits.numpy(), labels.numpy(), 255, 0.7, min_kept, want_grad=True)
+    if g["loss"] == "nan":
+        assert np.isnan(out["loss"])
+        return
+    assert abs(out["loss"] - g["loss"]) < 1e-5 * abs(g["loss"])
+    assert int(out["kept"].sum()) == g["kept_count"]
+    assert _sha(out["kept"].astype(np.uint8)) == g["kept_sha256"], "kept index set differs from the reference"
+    assert abs(float(np.abs(out["dlogits"]).sum()) - g["grad_abs_sum"]) < 1e-4 * g["grad_abs_sum"]
+
+
+@pytest.mark.parametrize("regime", OHEM_REGIMES)
+def test_torch_oracle_ohem_vs_golden_and_c(regime):
+    from oracle import c_oracle, torch_ref
+    logits, labels, min_kept = ohem_case(regime)
+    g = GOLD["ohem"][regime]
+    loss, valid, thr = torch_ref.ohem_ce(logits, labels, 255, 0.7, min_kept, return_aux=True)
+    out = c_oracle.ohem(logits.numpy(), labels.numpy(), 255, 0.7, min_kept)
+    if g["loss"] == "nan":
+        assert torch.isnan(loss)
+        return
+    assert abs(float(loss) - g["loss"]) < 1e-6 * abs(g["loss"])
+    assert np.array_equal(valid.numpy(), out["kept"])
+
+
+def test_ohem_weighted_and_focal_vs_golden():
+    from oracle import c_oracle, torch_ref
+    from torchseg_b200.seg_opr.loss_opr import ProbOhemCrossEntropy2d
+    logits, labels, min_kept = ohem_case("B")
+    w = np.array(ProbOhemCrossEntropy2d.CITYSCAPES_WEIGHT, np.float32)
+    out = c_oracle.ohem(logits.numpy(), labels.numpy(), 255, 0.7, min_kept, class_weight=w)
+    assert abs(out["loss"] - GOLD["ohem"]["B_weighted"]["loss"]) < 1e-5 * abs(GOLD["ohem"]["B_weighted"]["loss"])
+    g = torch.Generator().manual_seed(10)
+    pred = torch.randn(2, 1, 32, 40, generator=g)
+    tgt = torch.randint(0, 2, (2, 32, 40), generator=g)
+    tgt[:, :3] = 255
+    assert abs(float(torch_ref.sigmoid_focal(pred, tgt, 255)) - GOLD["focal"]["loss"]) < 1e-6
+
+
+def _ref_sd(build, seed):
+    torch.manual_seed(seed)
+    m = build()
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def test_torch_oracle_bisenet_vs_golden():
+    """same seed → same initial weights (our module mirrors the reference's construction order) → same loss"""
+    from oracle import torch_ref
+    from torchseg_b200.networks import BiSeNet
+    x, y, min_kept, seed = bisenet_case()
+    m, sd = _ref_sd(lambda: BiSeNet(19, True, None, None, torch.nn.BatchNorm2d), seed)
+    g = GOLD["bisenet_r18"]
+    assert sum(p.numel() for p in m.parameters()) == g["n_params"] and len(sd) == g["n_state"]
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    loss, _ = torch_ref.bisenet_r18_loss(x, y, sd, min_kept)
+    assert abs(float(loss) - g["loss"]) < 1e-5 * g["loss"]
+    loss.backward()
+    for n, ref in g["grad_norms"].items():
+        assert abs(float(sd[n].grad.norm()) - ref) < 1e-4 * ref, n
+
+
+def test_torch_oracle_fcn_r18_vs_golden():
+    """BASELINE configs[0] (plumbing case): FCN-32s R18, 2 x 256 x 256, CPU"""
+    from oracle import torch_ref
+    from torchseg_b200.networks import FCN
+    x, y, seed = fcn_case()
+    torch.manual_seed(seed)
+    m = FCN(19, backbone="R18")
+    sd = {}
+    for k, v in m.state_dict().items():   # reference key names: backbone.*, head.cbr.*, head.conv1x1.*
+        sd[k] = v.detach().clone()
+    loss = torch_ref.fcn_r18_loss(x, y, sd)
+    assert abs(float(loss) - GOLD["fcn_r18"]["loss"]) < 1e-5 * GOLD["fcn_r18"]["loss"]
+
+
+def test_exp_det_properties():
+    from oracle import c_oracle
+    assert c_oracle.exp_det(0.0) == 1.0
+    assert c_oracle.exp_det(-200.0) == 0.0
+    xs = np.linspace(-80, 0, 2001).astype(np.float32)
+    e = np.array([c_oracle.exp_det(float(v)) for v in xs])
+    r = np.exp(xs.astype(np.float64))
+    assert np.max(np.abs(e - r) / r) < 4e-7
+    assert np.all(np.diff(e) >= 0)  # monotone
+
+
+def test_bilinear_oracle_matches_aten():
+    from oracle import c_oracle
+    g = torch.Generator().manual_seed(4)
+    lo = torch.randn(2, 6, 9, 32, generator=g)
+    ref = torch.nn.functional.interpolate(lo[..., :19].permute(0, 3, 1, 2), scale_factor=8, mode="bilinear", align_corners=True)
+    out = c_oracle.bilinear_nhwc_to_nchw(lo.numpy(), 19, 48, 72)
+    assert np.max(np.abs(out - ref.numpy())) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# live reference (authoring container only)
+# ---------------------------------------------------------------------------------------------------------------
+def _live():
+    from oracle import reference_live as rl
+    if not rl.available():
+        pytest.skip("/root/reference not present (GPU box): pinned by tests/golden instead")
+    return rl
+
+
+def test_oracle_vs_live_reference_ohem():
+    rl = _live()
+    from oracle import c_oracle
+    lo = rl.load_loss_opr()
+    for regime in ["A", "B", "C", "D"]:
+        for seed in (1, 2, 3):
+            logits, labels, min_kept = ohem_case(regime, seed=seed, H=32, W=40)
+            crit = lo.ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=False)
+            x = logits.clone().requires_grad_(True)
+            loss = crit(x, labels)
+            loss.backward()
+            kept_ref = (x.grad.abs().sum(dim=1) > 0).reshape(-1).numpy()
+            out = c_oracle.ohem(logits.numpy(), labels.numpy(), 255, 0.7, min_kept, want_grad=True)
+            assert np.array_equal(out["kept"], kept_ref), (regime, seed)
+            assert abs(out["loss"] - float(loss)) < 1e-5 * abs(float(loss))
+            assert np.max(np.abs(out["dlogits"] - x.grad.numpy())) < 1e-6
+
+
+def test_oracle_vs_live_reference_bisenet_exact():
+    rl = _live()
+    from oracle import torch_ref
+    net = rl.load_network('bisenet/cityscapes.bisenet.R18')
+    lo = rl.load_loss_opr()
+    x, y, min_kept, seed = bisenet_case(N=2, HW=64, seed=5)
+    torch.manual_seed(seed)
+    crit = lo.ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=False)
+    m = net.BiSeNet(19, True, crit, None, torch.nn.BatchNorm2d)
+    m.train()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    loss_ref = m(x, y)
+    loss_ref.backward()
+    loss, _ = torch_ref.bisenet_r18_loss(x, y, sd, min_kept)
+    loss.backward()
+    assert float(loss) == float(loss_ref)
+    for n, p in m.named_parameters():
+        assert torch.equal(p.grad, sd[n].grad), n
+
+
+def test_module_key_names_match_reference():
+    """checkpoint compatibility: our BiSeNet exposes exactly the reference's state_dict keys and shapes (App. D)"""
+    rl = _live()
+    from torchseg_b200.networks import BiSeNet
+    net = rl.load_network('bisenet/cityscapes.bisenet.R18')
+    ref = net.BiSeNet(19, True, None, None, torch.nn.BatchNorm2d).state_dict()
+    ours = BiSeNet(19, True, None, None, torch.nn.BatchNorm2d).state_dict()
+    assert list(ref.keys()) == list(ours.keys())
+    for k in ref:
+        assert ref[k].shape == ours[k].shape, k

@@ -1,0 +1,95 @@
+"""Generate tests/golden/*.json from the LIVE reference (/root/reference, authoring container only).
+
+The reference ships no golden vectors; these fixtures pin the oracle to outputs of the reference
+modules themselves on seeded synthetic inputs. Inputs are regenerated from seeds (torch CPU generator), only
+outputs are stored. Run: python tools/make_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+from oracle import reference_live as rl  # noqa: E402
+from golden_cases import ohem_case, bisenet_case, fcn_case, OHEM_REGIMES  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(t):
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+def main():
+    assert rl.available(), "needs /root/reference"
+    torch.set_num_threads(8)
+    lo = rl.load_loss_opr()
+    gold = {"ohem": {}, "torch": torch.__version__}
+    for regime in OHEM_REGIMES:
+        logits, labels, min_kept = ohem_case(regime)
+        crit = lo.ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=False)
+        x = logits.clone().requires_grad_(True)
+        loss = crit(x, labels)
+        entry = {"loss": float(loss) if loss == loss else "nan", "min_kept": min_kept}
+        if loss == loss:
+            loss.backward()
+            kept = (x.grad.abs().sum(dim=1) > 0).reshape(-1)   # pixels that received gradient == kept set
+            entry["kept_count"] = int(kept.sum())
+            entry["kept_sha256"] = sha(kept.to(torch.uint8))
+            entry["grad_abs_sum"] = float(x.grad.abs().sum())
+        gold["ohem"][regime] = entry
+    # weighted variant (use_weight=True, loss_opr.py:57-63)
+    logits, labels, min_kept = ohem_case("B")
+    crit = lo.ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=True)
+    gold["ohem"]["B_weighted"] = {"loss": float(crit(logits, labels)), "min_kept": min_kept}
+    # focal
+    g = torch.Generator().manual_seed(10)
+    pred = torch.randn(2, 1, 32, 40, generator=g)
+    tgt = torch.randint(0, 2, (2, 32, 40), generator=g)
+    tgt[:, :3] = 255
+    gold["focal"] = {"loss": float(lo.SigmoidFocalLoss(255)(pred, tgt))}
+
+    # BiSeNet-R18 tiny step through the reference network.py
+    net = rl.load_network('bisenet/cityscapes.bisenet.R18')
+    x, y, min_kept, seed = bisenet_case()
+    torch.manual_seed(seed)
+    crit = lo.ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=False)
+    m = net.BiSeNet(19, True, crit, None, nn.BatchNorm2d)
+    m.train()
+    loss = m(x, y)
+    loss.backward()
+    gn = {n: float(p.grad.norm()) for n, p in m.named_parameters()
+          if n in ("context_path.conv1.weight", "spatial_path.conv_7x7.conv.weight", "heads.2.conv_1x1.weight", "ffm.conv_1x1.conv.weight")}
+    gold["bisenet_r18"] = {"loss": float(loss), "grad_norms": gn, "n_params": sum(p.numel() for p in m.parameters()),
+                           "n_state": len(m.state_dict())}
+
+    # FCN-32s R18 (BASELINE configs[0]) assembled from the reference's own resnet18 + _FCNHead
+    fcn = rl.load_network('fcn/voc.fcn32s.R101_v1c', num_classes=19, aux_loss_ratio=0.5)
+    resnet = rl.load_resnet()
+    x, y, seed = fcn_case()
+    torch.manual_seed(seed)
+    backbone = resnet.resnet18(None, norm_layer=nn.BatchNorm2d, bn_eps=1e-5, bn_momentum=0.1, deep_stem=False, stem_width=64)
+    head = fcn._FCNHead(512, 19, True, nn.BatchNorm2d)
+    aux_head = fcn._FCNHead(256, 19, True, nn.BatchNorm2d)
+    for h in (head, aux_head):
+        h.dropout.p = 0.0
+    import torch.nn.functional as F
+    blocks = backbone(x)
+    pred = F.interpolate(head(blocks[-1]), scale_factor=32, mode='bilinear', align_corners=True)
+    aux = F.interpolate(aux_head(blocks[-2]), scale_factor=16, mode='bilinear', align_corners=True)
+    ce = nn.CrossEntropyLoss(ignore_index=255)
+    gold["fcn_r18"] = {"loss": float(ce(pred, y) + 0.5 * ce(aux, y))}
+
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "reference_outputs.json"), "w") as f:
+        json.dump(gold, f, indent=1, sort_keys=True)
+    print(json.dumps(gold, indent=1)[:1500])
+
+
+if __name__ == "__main__":
+    main()

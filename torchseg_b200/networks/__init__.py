@@ -1,1 +1,2 @@
 from .bisenet import BiSeNet, SpatialPath, BiSeNetHead
+from .fcn import FCN
