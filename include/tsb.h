@@ -41,6 +41,9 @@ const char* tsb_last_error(void);
 int tsb_version(void);          /* 10000*major + 100*minor + patch */
 /* number of kernels launched by this library from the calling process since load (all threads) */
 long long tsb_launch_count(void);
+/* debug / A-B switches of the convolution path: key 1 = UMMA descriptor base_offset for row-shifted taps,
+ * 2 = allow row tiles, 3 = allow resident weights, 4 = use the persistent kernel (0 → first-generation kernel) */
+int tsb_debug_set(int key, int value);
 
 /* ================================================================================================
  * OHEM cross-entropy — replaces ProbOhemCrossEntropy2d.forward, furnace/seg_opr/loss_opr.py:68-98

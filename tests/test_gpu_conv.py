@@ -20,6 +20,11 @@ CASES = [
     (3, 64, 17, 23, 64, 3, 2, 1, 1),       # odd sizes, stride 2
     (2, 128, 12, 12, 256, 3, 1, 4, 4),     # dilation 4
     (4, 512, 1, 1, 128, 1, 1, 0, 1),       # global-context conv on a 1x1 map
+    (1, 64, 6, 160, 64, 3, 1, 1, 1),       # long rows → row tiles (3 taps share one halo load)
+    (2, 128, 5, 200, 128, 3, 1, 2, 2),     # row tiles + dilation 2, ragged width
+    (1, 64, 7, 260, 128, 3, 2, 1, 1),      # row tiles, stride 2 (parity views), Q = 130
+    (1, 64, 3, 300, 64, 3, 1, 4, 4),       # row tiles + dilation 4 (span 8)
+    (1, 128, 4, 256, 64, 1, 1, 0, 1),      # 1x1 → flat GEMM, resident weights
 ]
 
 

@@ -28,6 +28,7 @@ D = c_double
 
 # name -> argtypes (the trailing stream argument is included)
 _SIGS = {
+    "tsb_debug_set": [I, I],
     "tsb_ohem_begin": [P, P],
     "tsb_ohem_ptarget": [P, I, L, L, L, L, P, I, I, I, I, I, F, P, P, P, P],
     "tsb_ohem_ptarget_up": [P, I, I, I, P, I, I, I, I, I, F, P, P, P, P],

@@ -12,25 +12,18 @@
 // Replaces the cuDNN lowering of nn.Conv2d at /root/reference/furnace/seg_opr/seg_oprs.py:29-31,
 // /root/reference/furnace/base_model/resnet.py:11-14,126 and the heads of
 // /root/reference/model/bisenet/cityscapes.bisenet.R18/network.py:145-161 (SURVEY.md §8 a1,a2).
-#include <cuda.h>
-#include <mutex>
-
+#include "conv_common.cuh"
+#include "conv_v2.cuh"
 #include "sm100_ptx.cuh"
-#include "tsb_common.cuh"
 
 using namespace sm100;
+using namespace convhost;
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------
 // parameter blocks (passed as __grid_constant__)
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxTaps = 16;
-struct Tap {
-    int dh, dw;  // offset of the TMA box origin relative to the output-tile origin (map coordinates)
-    int map;     // which A tensor map (stride-2 parity view)
-    int bk;      // offset of this tap along the K dimension of B
-};
 
 struct alignas(64) KmParams {
     CUtensorMap mapA[4];
@@ -372,94 +365,6 @@ __global__ void __launch_bounds__(kThreadsConv, 1) wgrad_mnmajor_kernel(const __
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
-// ------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &f, 12000, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(f);
-    });
-    return fn;
-}
-
-// rank-4 bf16 map; strides in BYTES for dims 1..3; zero OOB fill; 128B swizzle
-int encode_4d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1,
-              uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) TSB_FAIL(TSB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    cuuint64_t dims[4] = {d0, d1, d2, d3};
-    cuuint64_t strides[3] = {s1, s2, s3};
-    cuuint32_t box[4] = {b0, b1, b2, b3};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        TSB_FAIL(TSB_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) box=(%u,%u,%u,%u)",
-                 (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3,
-                 (unsigned long long)s1, (unsigned long long)s2, (unsigned long long)s3, b0, b1, b2, b3);
-    return TSB_OK;
-}
-int encode_2d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t s1, uint32_t b0, uint32_t b1) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) TSB_FAIL(TSB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    cuuint64_t dims[2] = {d0, d1};
-    cuuint64_t strides[1] = {s1};
-    cuuint32_t box[2] = {b0, b1};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        TSB_FAIL(TSB_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d dims=(%llu,%llu) stride=%llu box=(%u,%u)", (int)r,
-                 (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)s1, b0, b1);
-    return TSB_OK;
-}
-
-inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-inline int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
-inline int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
-
-// spatial tile of `npx` (128 or 64) pixels: TW x TH with TW a power of two
-void pick_tile(int Q, int npx, int* TW, int* TH) {
-    int tw = pow2ceil(Q);
-    int pref = (npx == 128) ? 16 : 8;
-    if (tw > pref) tw = pref;
-    if (tw > npx) tw = npx;
-    *TW = tw;
-    *TH = npx / tw;
-}
-
-// A-operand maps over an NHWC bf16 tensor [N,H,W,Cs] (channel count Cc, channel stride cs), for a conv of
-// stride `st`: st==1 → 1 map; st==2 → 4 parity views (ph,pw) of dims ceil((H-ph)/2) x ceil((W-pw)/2).
-int encode_act_maps(CUtensorMap* maps, const void* base, int N, int H, int W, int Cc, int cs, int st, int TW, int TH) {
-    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base);
-    if (st == 1) {
-        return encode_4d(&maps[0], b, Cc, W, H, N, (uint64_t)cs * 2, (uint64_t)W * cs * 2, (uint64_t)H * W * cs * 2, 64, TW,
-                         TH, 1);
-    }
-    for (int ph = 0; ph < 2; ++ph)
-        for (int pw = 0; pw < 2; ++pw) {
-            int Hh = (H - ph + 1) / 2, Ww = (W - pw + 1) / 2;
-            if (Hh <= 0 || Ww <= 0) { Hh = Hh > 0 ? Hh : 1; Ww = Ww > 0 ? Ww : 1; }
-            int rc = encode_4d(&maps[ph * 2 + pw], b + ((long long)ph * W + pw) * cs, Cc, Ww, Hh, N, (uint64_t)2 * cs * 2,
-                               (uint64_t)2 * W * cs * 2, (uint64_t)H * W * cs * 2, 64, TW, TH, 1);
-            if (rc) return rc;
-        }
-    return TSB_OK;
-}
-
 template <int BN, int STAGES>
 int launch_km(const KmParams& prm, int tiles, int n_tiles, cudaStream_t st) {
     using L = KmSmem<BN, STAGES>;
@@ -494,18 +399,6 @@ int launch_wg(const WgParams& prm, int splits, int co_tiles, int groups, cudaStr
     return TSB_OK;
 }
 
-int check_shape(const tsb_conv_shape* s, const char* who) {
-    TSB_REQUIRE(s != nullptr, "%s: null shape", who);
-    TSB_REQUIRE(s->N > 0 && s->H > 0 && s->W > 0 && s->C > 0 && s->K > 0, "%s: bad sizes", who);
-    TSB_REQUIRE(s->R == s->S && s->R >= 1 && s->R * s->S <= kMaxTaps, "%s: filter must be square with R*S <= %d", who, kMaxTaps);
-    TSB_REQUIRE(s->stride == 1 || s->stride == 2, "%s: stride must be 1 or 2", who);
-    TSB_REQUIRE(s->dil >= 1 && s->pad >= 0, "%s: bad pad/dil", who);
-    int P = (s->H + 2 * s->pad - s->dil * (s->R - 1) - 1) / s->stride + 1;
-    int Q = (s->W + 2 * s->pad - s->dil * (s->S - 1) - 1) / s->stride + 1;
-    TSB_REQUIRE(P == s->P && Q == s->Q, "%s: P,Q (%d,%d) inconsistent with geometry (%d,%d)", who, s->P, s->Q, P, Q);
-    return TSB_OK;
-}
-
 }  // namespace
 
 // =================================================================================================
@@ -513,7 +406,7 @@ int check_shape(const tsb_conv_shape* s, const char* who) {
 // =================================================================================================
 extern "C" int tsb_conv2d_fprop(const tsb_conv_shape* s, const void* x, int xcs, const void* w, const float* bias,
                                 void* y, int ydtype, int ycs, float* sum, float* sumsq, tsb_stream_t stream) {
-    int rc = check_shape(s, "tsb_conv2d_fprop");
+    int rc = check_conv_shape(s, "tsb_conv2d_fprop");
     if (rc) return rc;
     TSB_REQUIRE(x && w && y, "tsb_conv2d_fprop: null pointer");
     TSB_REQUIRE(s->C % 64 == 0, "tsb_conv2d_fprop: C must be a multiple of 64 (got %d)", s->C);
@@ -566,13 +459,26 @@ extern "C" int tsb_conv2d_fprop(const tsb_conv_shape* s, const void* x, int xcs,
     prm.out_f32 = (ydtype == TSB_F32);
     prm.accumulate = 0;
     prm.bias = bias; prm.sum = sum; prm.sumsq = sumsq; prm.out = y;
+    if (convv2::g_enabled) {
+        convv2::Desc d;
+        memset(&d, 0, sizeof(d));
+        d.act = x; d.aN = N; d.aH = H; d.aW = W; d.aC = s->C; d.acs = xcs; d.act_stride = s->stride; d.flat = flat;
+        for (int t = 0; t < nt; ++t) d.taps[t] = prm.taps[t];
+        d.ntaps = nt; d.kchunks = s->C / 64;
+        d.w = w; d.w_rows = s->K; d.w_k = (long long)s->R * s->S * s->C; d.ncols = kst;
+        d.Nl = N; d.Pl = P; d.Ql = Q;
+        d.out_n_stride = prm.out_n_stride; d.out_p_stride = prm.out_p_stride; d.out_q_stride = prm.out_q_stride; d.out_base = 0;
+        d.k_real = s->K; d.k_store = kst; d.out_f32 = prm.out_f32; d.accumulate = 0;
+        d.bias = bias; d.sum = sum; d.sumsq = sumsq; d.out = y;
+        return convv2::launch(d, st);
+    }
     int tiles = prm.tiles_w * prm.tiles_h * N;
     return launch_km_auto(prm, w, s->K, (long long)s->R * s->S * s->C, kst, tiles, st);
 }
 
 extern "C" int tsb_conv2d_dgrad(const tsb_conv_shape* s, const void* dy, int dycs, const void* wt, void* dx, int dxcs,
                                 int accumulate, tsb_stream_t stream) {
-    int rc = check_shape(s, "tsb_conv2d_dgrad");
+    int rc = check_conv_shape(s, "tsb_conv2d_dgrad");
     if (rc) return rc;
     TSB_REQUIRE(dy && wt && dx, "tsb_conv2d_dgrad: null pointer");
     TSB_REQUIRE(s->K % 64 == 0, "tsb_conv2d_dgrad: K must be a multiple of 64 (pad the classifier to 64), got %d", s->K);
@@ -638,6 +544,22 @@ extern "C" int tsb_conv2d_dgrad(const tsb_conv_shape* s, const void* dy, int dyc
         prm.out_f32 = 0;
         prm.accumulate = accumulate;
         prm.out = dx;
+        if (convv2::g_enabled) {
+            convv2::Desc d;
+            memset(&d, 0, sizeof(d));
+            d.act = dy; d.aN = N; d.aH = P; d.aW = Q; d.aC = s->K; d.acs = dycs; d.act_stride = 1; d.flat = flat;
+            for (int t = 0; t < nt; ++t) d.taps[t] = prm.taps[t];
+            d.ntaps = nt; d.kchunks = s->K / 64;
+            d.w = wt; d.w_rows = s->C; d.w_k = (long long)s->R * s->S * s->K; d.ncols = s->C;
+            d.Nl = N; d.Pl = Hl; d.Ql = Wl;
+            d.out_n_stride = prm.out_n_stride; d.out_p_stride = prm.out_p_stride; d.out_q_stride = prm.out_q_stride;
+            d.out_base = prm.out_base;
+            d.k_real = s->C; d.k_store = s->C; d.out_f32 = 0; d.accumulate = accumulate;
+            d.out = dx;
+            rc = convv2::launch(d, st);
+            if (rc) return rc;
+            continue;
+        }
         int tiles = prm.tiles_w * prm.tiles_h * N;
         rc = launch_km_auto(prm, wt, s->C, (long long)s->R * s->S * s->K, s->C, tiles, st);
         if (rc) return rc;
@@ -674,7 +596,7 @@ int wgrad_common(WgParams& prm, int N, int P, int Q, int K, cudaStream_t st) {
 
 extern "C" int tsb_conv2d_wgrad(const tsb_conv_shape* s, const void* x, int xcs, const void* dy, int dycs, float* dw,
                                 tsb_stream_t stream) {
-    int rc = check_shape(s, "tsb_conv2d_wgrad");
+    int rc = check_conv_shape(s, "tsb_conv2d_wgrad");
     if (rc) return rc;
     TSB_REQUIRE(x && dy && dw, "tsb_conv2d_wgrad: null pointer");
     TSB_REQUIRE(s->C % 64 == 0, "tsb_conv2d_wgrad: C must be a multiple of 64 (got %d)", s->C);
@@ -715,6 +637,16 @@ extern "C" int tsb_conv2d_wgrad(const tsb_conv_shape* s, const void* x, int xcs,
     prm.C = s->C;
     prm.dw_row_stride = (long long)s->R * s->S * s->C;
     prm.dw = dw;
+    if (convv2::g_enabled && !flat && s->R > 1) {
+        convv2::WgradDesc d;
+        memset(&d, 0, sizeof(d));
+        d.x = x; d.dy = dy; d.N = N; d.H = H; d.W = W; d.C = s->C; d.xcs = xcs; d.P = P; d.Q = Q; d.K = s->K; d.dycs = dycs;
+        d.stride = s->stride;
+        for (int t = 0; t < nt; ++t) d.taps[t] = prm.taps[t];
+        d.ntaps = nt; d.dw_row_stride = prm.dw_row_stride; d.dw = dw;
+        rc = convv2::launch_wgrad_rows(d, st);
+        if (rc != TSB_ERR_UNSUPPORTED) return rc;
+    }
     return wgrad_common(prm, N, P, Q, s->K, st);
 }
 
@@ -752,6 +684,19 @@ extern "C" int tsb_conv_stem_fprop(const void* xs2d, int N, int H, int W, const 
     prm.k_real = K; prm.k_store = K;
     prm.out_f32 = 0; prm.accumulate = 0;
     prm.sum = sum; prm.sumsq = sumsq; prm.out = y;
+    if (convv2::g_enabled) {
+        convv2::Desc d;
+        memset(&d, 0, sizeof(d));
+        d.act = xs2d; d.aN = N; d.aH = H2; d.aW = W2; d.aC = 64; d.acs = 16; d.act_stride = 1; d.stem = 1;
+        for (int a = 0; a < 4; ++a) d.taps[a] = prm.taps[a];
+        d.ntaps = 4; d.kchunks = 1;
+        d.w = wp; d.w_rows = K; d.w_k = 256; d.ncols = K;
+        d.Nl = N; d.Pl = H2; d.Ql = W2;
+        d.out_n_stride = prm.out_n_stride; d.out_p_stride = prm.out_p_stride; d.out_q_stride = prm.out_q_stride;
+        d.k_real = K; d.k_store = K;
+        d.sum = sum; d.sumsq = sumsq; d.out = y;
+        return convv2::launch(d, (cudaStream_t)stream);
+    }
     int tiles = prm.tiles_w * prm.tiles_h * N;
     return launch_km_auto(prm, wp, K, 256, K, tiles, (cudaStream_t)stream);
 }

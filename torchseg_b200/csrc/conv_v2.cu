@@ -1,0 +1,652 @@
+// Persistent implicit-GEMM convolution (fprop / dgrad / stem), second generation.
+//
+// Versus igemm_kmajor_kernel (conv_tcgen05.cu):
+//   * persistent CTAs (one per SM) striding over output tiles of one N-tile → prologue (barriers, TMEM alloc,
+//     descriptor prefetch) paid once, BN statistics accumulated in shared memory across all tiles of the CTA;
+//   * the B operand (packed weights of this N-tile) stays RESIDENT in shared memory when it fits (C=64 layers,
+//     1x1 convs, stems) instead of being re-fetched from L2 for every tile;
+//   * ROW tiles (TH = 1, TW = 128): the horizontal taps of one filter row share ONE TMA box of TW+span pixels; the
+//     taps are addressed by shifting the UMMA descriptor start by whole 128-byte rows (descriptor base_offset =
+//     (addr >> 7) & 7), cutting the L2→SM activation traffic of a 3x3 layer 3x;
+//   * two TMEM accumulator buffers: the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "conv_common.cuh"
+#include "conv_v2.cuh"
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+using namespace convhost;
+
+namespace {
+
+constexpr int kThreads = 384;  // 4 control warps + 8 epilogue warps
+constexpr int kMaxStages = 8;
+constexpr int kAStageBytes = 17 * 1024;  // (128 + 8) pixel rows x 128 B, rounded up to a 1024-byte multiple
+
+struct TapGroup {
+    int dh, dw0, map, ntaps;
+    int row_off[3];  // pixel-row offset of each tap inside the group's box
+    int bk[3];       // K offset of each tap in B (streamed mode)
+    int tap_idx[3];  // global tap index (resident mode)
+};
+
+struct alignas(64) V2Params {
+    CUtensorMap mapA[4];
+    CUtensorMap mapB;
+    TapGroup groups[kMaxTaps];
+    int a_bytes[4];  // TMA bytes of one A box per map
+    int ngroups, ntaps_total, kchunks;
+    int tiles_w, tiles_h, m_tiles;
+    int tw_shift, TW, TH;
+    int P, Q;
+    long long out_n_stride, out_p_stride, out_q_stride, out_base;
+    int k_real, k_store, out_f32, accumulate;
+    const float* bias;
+    float* sum;
+    float* sumsq;
+    void* out;
+    // shared-memory plan
+    int nstages, stage_bytes, res_bytes, use_base_offset;
+};
+
+template <int BN, bool RES>
+__global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_constant__ V2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* res_b = smem;                       // resident weights (RES)
+    uint8_t* stages = smem + p.res_bytes;        // ring of A (+B) stages
+    uint8_t* tail = stages + p.nstages * p.stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;  // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint64_t* b_ready = tmem_empty + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_ready + 1);
+    float* s_stats = reinterpret_cast<float*>(tail + 256);  // [2*BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * BN;
+    const int my_tiles = (p.m_tiles > (int)blockIdx.x) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int iters_per_tile = p.ngroups * p.kchunks;
+    constexpr int kBTile = BN * 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapB);
+        tma_prefetch_desc(&p.mapA[0]);
+        for (int s = 0; s < p.nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+        mbar_init(b_ready, 1);
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc<2 * BN>(tmem_ptr);
+    } else if (warp == 3) {
+        for (int i = lane; i < 2 * BN; i += 32) s_stats[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0 && my_tiles > 0) {
+            if (RES) {  // weights of this N-tile: loaded once per CTA
+                mbar_arrive_expect_tx(b_ready, (uint32_t)(p.ntaps_total * p.kchunks * kBTile));
+                for (int g = 0; g < p.ngroups; ++g)
+                    for (int t = 0; t < p.groups[g].ntaps; ++t)
+                        for (int kc = 0; kc < p.kchunks; ++kc)
+                            tma_load_2d(res_b + (p.groups[g].tap_idx[t] * p.kchunks + kc) * kBTile, &p.mapB, b_ready,
+                                        p.groups[g].bk[t] + kc * 64, n0);
+            }
+            int it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                const int tw_i = tile % p.tiles_w;
+                const int th_i = (tile / p.tiles_w) % p.tiles_h;
+                const int n_img = tile / (p.tiles_w * p.tiles_h);
+                const int q0 = tw_i * p.TW, p0 = th_i * p.TH;
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const TapGroup G = p.groups[g];
+                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                        const int s = it % p.nstages;
+                        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        uint8_t* a_s = stages + s * p.stage_bytes;
+                        const uint32_t bytes = (uint32_t)p.a_bytes[G.map] + (RES ? 0u : (uint32_t)(G.ntaps * kBTile));
+                        mbar_arrive_expect_tx(&full_bar[s], bytes);
+                        tma_load_4d(a_s, &p.mapA[G.map], &full_bar[s], kc * 64, q0 + G.dw0, p0 + G.dh, n_img);
+                        if (!RES) {
+                            for (int t = 0; t < G.ntaps; ++t)
+                                tma_load_2d(a_s + kAStageBytes + t * kBTile, &p.mapB, &full_bar[s], G.bk[t] + kc * 64, n0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && my_tiles > 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+            if (RES) { mbar_wait(b_ready, 0); tc_fence_after(); }
+            int it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int buf = i & 1;
+                mbar_wait(&tmem_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * BN;
+                uint32_t first = 1;
+                for (int g = 0; g < p.ngroups; ++g) {
+                    const TapGroup G = p.groups[g];
+                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+                        const int s = it % p.nstages;
+                        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(stages + s * p.stage_bytes);
+                        for (int t = 0; t < G.ntaps; ++t) {
+                            const uint32_t a_addr = a_base + G.row_off[t] * 128;
+                            const uint32_t b_addr = RES ? smem_u32(res_b + (G.tap_idx[t] * p.kchunks + kc) * kBTile)
+                                                        : a_base + kAStageBytes + t * kBTile;
+                            // start shifted by whole 128-byte rows: swizzle phase carried in base_offset
+                            const uint64_t bo = p.use_base_offset ? ((uint64_t)((a_addr >> 7) & 7u) << 49) : 0ull;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024) | bo;
+                                uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                                umma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                        }
+                        umma_commit(&empty_bar[s]);
+                    }
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // 8 epilogue warps. TMEM lane quarter = warp % 4 (hardware rule); the column range is split by (warp-4)/4:
+        //   BN = 64 : each warp owns ONE 32-column chunk of every tile → BN statistics are plain per-thread running
+        //             sums over all tiles of the CTA (no shuffles / atomics per tile), reduced once at the end;
+        //   BN = 128: each warp owns a 64-column half (2 chunks) with a per-tile shuffle reduce-scatter.
+        const int quarter = warp & 3;
+        const int chalf = (warp - 4) >> 2;
+        const int m = quarter * 32 + lane;
+        const bool do_stats = (p.sum != nullptr);
+        constexpr bool kRunning = (BN == 64);
+        constexpr int kChunksPerWarp = kRunning ? 1 : 2;
+        float run1[kRunning ? 32 : 1], run2[kRunning ? 32 : 1];
+#pragma unroll
+        for (int q = 0; q < (kRunning ? 32 : 1); ++q) { run1[q] = 0.f; run2[q] = 0.f; }
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int tw_i = tile % p.tiles_w;
+            const int th_i = (tile / p.tiles_w) % p.tiles_h;
+            const int n_img = tile / (p.tiles_w * p.tiles_h);
+            const int pp = th_i * p.TH + (m >> p.tw_shift), qq = tw_i * p.TW + (m & (p.TW - 1));
+            const bool valid = (pp < p.P) && (qq < p.Q);
+            const long long pix_off = p.out_base + (long long)n_img * p.out_n_stride + (long long)pp * p.out_p_stride +
+                                      (long long)qq * p.out_q_stride;
+            const int buf = i & 1;
+            if (iters_per_tile > 0) {
+                mbar_wait(&tmem_full[buf], ((uint32_t)i >> 1) & 1u);
+                tc_fence_after();
+            }
+            const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int jj = 0; jj < kChunksPerWarp; ++jj) {
+                const int j = chalf * kChunksPerWarp + jj;
+                uint32_t r[32];
+                if (iters_per_tile > 0) {
+                    tmem_ld_32x32b_x32(taddr + j * 32, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) r[q] = 0u;
+                }
+                if (jj == kChunksPerWarp - 1) {  // this warp's TMEM reads of the tile are done
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                const int col0 = n0 + j * 32;
+                float v[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (col0 + q < p.k_real) v[q] += __ldg(p.bias + col0 + q);
+                }
+                if (p.out_f32) {
+                    float* o = reinterpret_cast<float*>(p.out) + pix_off + col0;
+                    if (valid) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            if (col0 + g * 4 < p.k_store)
+                                *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    }
+                } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + col0;
+                    if (p.accumulate && valid) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (col0 + g * 8 < p.k_store) {
+                                float old[8];
+                                uint4 u = *reinterpret_cast<const uint4*>(o + g * 8);
+                                unpack8(u, old);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) v[g * 8 + q] += old[q];
+                            }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = bf16_round(v[q]);
+                    if (valid) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (col0 + g * 8 < p.k_store) *reinterpret_cast<uint4*>(o + g * 8) = pack8(&v[g * 8]);
+                    }
+                }
+                if (do_stats) {
+                    if (kRunning) {
+                        if (valid) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) { run1[q] += v[q]; run2[q] = fmaf(v[q], v[q], run2[q]); }
+                        }
+                    } else {
+                        float s1[32], s2[32];
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) { s1[q] = valid ? v[q] : 0.f; s2[q] = s1[q] * s1[q]; }
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            const bool upper = (lane & off) != 0;
+#pragma unroll
+                            for (int q = 0; q < off; ++q) {
+                                float send1 = upper ? s1[q] : s1[q + off];
+                                float keep1 = upper ? s1[q + off] : s1[q];
+                                float send2 = upper ? s2[q] : s2[q + off];
+                                float keep2 = upper ? s2[q + off] : s2[q];
+                                s1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                                s2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                            }
+                        }
+                        atomicAdd(&s_stats[j * 32 + lane], s1[0]);
+                        atomicAdd(&s_stats[BN + j * 32 + lane], s2[0]);
+                    }
+                }
+            }
+        }
+        if (do_stats) {
+            if (kRunning) {  // one warp reduce-scatter per CTA instead of one per tile
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                    for (int q = 0; q < off; ++q) {
+                        float send1 = upper ? run1[q] : run1[q + off];
+                        float keep1 = upper ? run1[q + off] : run1[q];
+                        float send2 = upper ? run2[q] : run2[q + off];
+                        float keep2 = upper ? run2[q + off] : run2[q];
+                        run1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                        run2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                    }
+                }
+                atomicAdd(&s_stats[chalf * 32 + lane], run1[0]);
+                atomicAdd(&s_stats[BN + chalf * 32 + lane], run2[0]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+            for (int i = threadIdx.x - 128; i < BN; i += 256) {
+                if (n0 + i < p.k_real) {
+                    atomicAdd(p.sum + n0 + i, s_stats[i]);
+                    atomicAdd(p.sumsq + n0 + i, s_stats[BN + i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad, row-tile variant: the horizontal taps of one filter row share ONE activation box.
+//   dW[co, (s, ci)] += Σ_px dY[px, co] · X[px + s·step, ci]      for the ntaps (<= 3) taps of the group
+// A = dYᵀ (MN-major, 2 boxes of 64 out-channels), B = ONE box of 64+span pixels x 64 in-channels (MN-major); the
+// taps are the N-groups of a single UMMA B descriptor whose leading-dimension byte offset is step·128 B (the same
+// smem rows, shifted) → N = 64·ntaps without re-loading the activations per tap.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWrStages = 8;
+constexpr int kWrABytes = 2 * 64 * 128;   // two 64-channel dY boxes of 64 pixels
+constexpr int kWrBBytes = 10 * 1024;      // (64 + 8) pixel rows x 128 B, rounded up
+constexpr int kWrStageBytes = kWrABytes + kWrBBytes;
+constexpr int kWrSmem = kWrStages * kWrStageBytes + 256 + 1024;
+
+struct WrGroup { int dh, dw0, map, ntaps, step; int tap_idx[3]; };
+struct alignas(64) WrParams {
+    CUtensorMap mapA;
+    CUtensorMap mapB[4];
+    WrGroup groups[kMaxTaps];
+    int b_bytes[4];
+    int ngroups, cchunks;
+    int tiles_w, tiles_h, total_tiles, tiles_per_split;
+    int TW;
+    int K, C;
+    long long dw_row_stride;
+    float* dw;
+};
+
+__global__ void __launch_bounds__(256, 1) wgrad_rows_kernel(const __grid_constant__ WrParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWrStages * kWrStageBytes);
+    uint64_t* empty_bar = full_bar + kWrStages;
+    uint64_t* tmem_full = empty_bar + kWrStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co0 = blockIdx.y * 128;
+    const int g = blockIdx.z / p.cchunks, cc = blockIdx.z - g * p.cchunks;
+    const WrGroup G = p.groups[g];
+    const int t_begin = blockIdx.x * p.tiles_per_split;
+    const int t_end = min(p.total_tiles, t_begin + p.tiles_per_split);
+    const int total_iters = t_end - t_begin;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapA);
+        tma_prefetch_desc(&p.mapB[G.map]);
+        for (int s = 0; s < kWrStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc<256>(tmem_ptr);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % kWrStages;
+                const uint32_t ph = (uint32_t)(it / kWrStages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                const int t = t_begin + it;
+                const int tw_i = t % p.tiles_w;
+                const int row = (t / p.tiles_w) % p.tiles_h;
+                const int n_img = t / (p.tiles_w * p.tiles_h);
+                const int q0 = tw_i * p.TW;
+                uint8_t* a_s = smem + s * kWrStageBytes;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(kWrABytes + p.b_bytes[G.map]));
+                tma_load_4d(a_s, &p.mapA, &full_bar[s], co0, q0, row, n_img);
+                tma_load_4d(a_s + 64 * 128, &p.mapA, &full_bar[s], co0 + 64, q0, row, n_img);  // OOB → zeros
+                tma_load_4d(a_s + kWrABytes, &p.mapB[G.map], &full_bar[s], cc * 64, q0 + G.dw0, row + G.dh, n_img);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 64 * G.ntaps, true, true);
+            const uint32_t b_lbo = (uint32_t)(G.ntaps > 1 ? G.step * 128 : 128);
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % kWrStages;
+                const uint32_t ph = (uint32_t)(it / kWrStages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * kWrStageBytes);
+                const uint32_t b_addr = a_addr + kWrABytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t da = make_smem_desc_sw128(a_addr + k * 2048, 64 * 128, 1024);
+                    uint64_t db = make_smem_desc_sw128(b_addr + k * 2048, b_lbo, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            if (total_iters > 0) umma_commit(tmem_full);
+        }
+    } else if (warp >= 4 && total_iters > 0) {
+        const int ew = warp - 4;
+        const int co = co0 + ew * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
+        for (int t = 0; t < G.ntaps; ++t) {
+            float* dst = p.dw + (long long)co * p.dw_row_stride + (long long)G.tap_idx[t] * p.C + cc * 64;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + t * 64 + half * 32, r);
+                tmem_ld_wait();
+                if (co < p.K) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        red_add_v4(dst + half * 32 + q * 4, __uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                   __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+int g_use_base_offset = 0;  // measured on B200: the swizzle XOR is taken from the absolute smem address bits, so row-shifted starts need NO base_offset
+int g_allow_rows = 1;
+int g_allow_resident = 1;
+
+template <int BN, bool RES>
+int launch_v2(const V2Params& prm, int grid_x, int n_tiles, size_t smem, cudaStream_t st) {
+    static size_t attr_bytes = 0;
+    if (smem > attr_bytes) {
+        TSB_CUDA_CALL(cudaFuncSetAttribute(igemm_v2_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_bytes = 227 * 1024;
+    }
+    igemm_v2_kernel<BN, RES><<<dim3(grid_x, n_tiles), kThreads, smem, st>>>(prm);
+    TSB_CUDA_CHECK_LAUNCH("igemm_v2");
+    return TSB_OK;
+}
+
+}  // namespace
+
+extern "C" int tsb_debug_set(int key, int value) {
+    if (key == 1) g_use_base_offset = value;
+    else if (key == 2) g_allow_rows = value;
+    else if (key == 3) g_allow_resident = value;
+    else if (key == 4) convv2::g_enabled = value;
+    else return TSB_ERR_ARG;
+    return TSB_OK;
+}
+
+namespace convv2 {
+
+int g_enabled = 1;
+
+int launch(const Desc& d, cudaStream_t st) {
+    V2Params prm;
+    memset(&prm, 0, sizeof(prm));
+    const int BN = (d.ncols <= 64) ? 64 : 128;
+    const int n_tiles = (d.ncols + BN - 1) / BN;
+    // ---- spatial tiling: row tiles when the output rows are long enough
+    int TW, TH;
+    const bool rows = g_allow_rows && !d.flat && d.Ql >= 96;
+    if (d.flat || rows) { TW = 128; TH = 1; }
+    else pick_tile(d.Ql, 128, &TW, &TH);
+    // ---- group the taps: same (map, dh) → one box, taps addressed by a row offset (row tiles only)
+    int span_map[4] = {0, 0, 0, 0};
+    int ng = 0;
+    for (int t = 0; t < d.ntaps; ++t) {
+        const Tap& T = d.taps[t];
+        int g = -1;
+        if (rows) {
+            for (int k = 0; k < ng; ++k)
+                if (prm.groups[k].map == T.map && prm.groups[k].dh == T.dh && prm.groups[k].ntaps < 3 &&
+                    abs(T.dw - prm.groups[k].dw0) <= 8) { g = k; break; }
+        }
+        if (g < 0) {
+            g = ng++;
+            prm.groups[g].map = T.map; prm.groups[g].dh = T.dh; prm.groups[g].dw0 = T.dw; prm.groups[g].ntaps = 0;
+        }
+        TapGroup& G = prm.groups[g];
+        if (T.dw < G.dw0) {  // keep dw0 = min dw of the group
+            int shift = G.dw0 - T.dw;
+            for (int k = 0; k < G.ntaps; ++k) G.row_off[k] += shift;
+            G.dw0 = T.dw;
+        }
+        G.row_off[G.ntaps] = T.dw - G.dw0;
+        G.bk[G.ntaps] = T.bk;
+        G.tap_idx[G.ntaps] = t;
+        G.ntaps++;
+    }
+    for (int g = 0; g < ng; ++g)
+        for (int k = 0; k < prm.groups[g].ntaps; ++k)
+            if (prm.groups[g].row_off[k] > span_map[prm.groups[g].map]) span_map[prm.groups[g].map] = prm.groups[g].row_off[k];
+    for (int m = 0; m < 4; ++m) {
+        TSB_REQUIRE(span_map[m] <= 8, "conv_v2: tap span too large");
+        prm.a_bytes[m] = (TW + span_map[m]) * TH * 128;
+    }
+    prm.ngroups = ng;
+    prm.ntaps_total = d.ntaps;
+    prm.kchunks = d.kchunks;
+    // ---- A tensor maps (box width = TW + span of the map)
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(d.act);
+    int rc;
+    if (d.stem) {
+        const uint64_t row = (uint64_t)(d.aW + 4) * 16 * 2;
+        rc = encode_4d(&prm.mapA[0], base, 64, (uint64_t)d.aW, (uint64_t)d.aH, (uint64_t)d.aN, 32, row, row * d.aH, 64, TW + span_map[0], TH, 1);
+        if (rc) return rc;
+    } else if (d.act_stride == 1) {
+        rc = encode_4d(&prm.mapA[0], base, d.aC, d.aW, d.aH, d.aN, (uint64_t)d.acs * 2, (uint64_t)d.aW * d.acs * 2,
+                       (uint64_t)d.aH * d.aW * d.acs * 2, 64, TW + span_map[0], TH, 1);
+        if (rc) return rc;
+    } else {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                int Hh = (d.aH - ph + 1) / 2, Ww = (d.aW - pw + 1) / 2;
+                if (Hh <= 0) Hh = 1;
+                if (Ww <= 0) Ww = 1;
+                rc = encode_4d(&prm.mapA[ph * 2 + pw], base + ((long long)ph * d.aW + pw) * d.acs, d.aC, Ww, Hh, d.aN,
+                               (uint64_t)2 * d.acs * 2, (uint64_t)2 * d.aW * d.acs * 2, (uint64_t)d.aH * d.aW * d.acs * 2, 64,
+                               TW + span_map[ph * 2 + pw], TH, 1);
+                if (rc) return rc;
+            }
+    }
+    rc = encode_2d(&prm.mapB, d.w, (uint64_t)d.w_k, (uint64_t)d.w_rows, (uint64_t)d.w_k * 2, 64, BN);
+    if (rc) return rc;
+    // ---- geometry / epilogue
+    prm.tiles_w = (d.Ql + TW - 1) / TW;
+    prm.tiles_h = (d.Pl + TH - 1) / TH;
+    prm.m_tiles = prm.tiles_w * prm.tiles_h * d.Nl;
+    prm.TW = TW; prm.TH = TH; prm.tw_shift = ilog2(TW);
+    prm.P = d.Pl; prm.Q = d.Ql;
+    prm.out_n_stride = d.out_n_stride; prm.out_p_stride = d.out_p_stride; prm.out_q_stride = d.out_q_stride;
+    prm.out_base = d.out_base;
+    prm.k_real = d.k_real; prm.k_store = d.k_store; prm.out_f32 = d.out_f32; prm.accumulate = d.accumulate;
+    prm.bias = d.bias; prm.sum = d.sum; prm.sumsq = d.sumsq; prm.out = d.out;
+    prm.use_base_offset = g_use_base_offset;
+    // ---- shared-memory plan
+    const int kBTile = BN * 128;
+    const long long res_need = (long long)d.ntaps * d.kchunks * kBTile;
+    const bool resident = g_allow_resident && res_need <= 112 * 1024 && prm.m_tiles > 0;
+    const int tail = 256 + 2 * BN * 4;
+    const int budget = 227 * 1024 - 1024 /*align*/ - tail;
+    int max_group_taps = 1;
+    for (int g = 0; g < ng; ++g) if (prm.groups[g].ntaps > max_group_taps) max_group_taps = prm.groups[g].ntaps;
+    prm.res_bytes = resident ? (int)res_need : 0;
+    prm.stage_bytes = kAStageBytes + (resident ? 0 : max_group_taps * kBTile);
+    int ns = (budget - prm.res_bytes) / prm.stage_bytes;
+    if (ns > kMaxStages) ns = kMaxStages;
+    TSB_REQUIRE(ns >= 2, "conv_v2: shared-memory plan needs at least 2 stages");
+    prm.nstages = ns;
+    const size_t smem = 1024 + (size_t)prm.res_bytes + (size_t)ns * prm.stage_bytes + tail;
+    int grid_x = tsb_num_sms() / n_tiles;
+    if (grid_x < 1) grid_x = 1;
+    if (grid_x > prm.m_tiles) grid_x = prm.m_tiles;
+    if (grid_x < 1) grid_x = 1;
+    if (BN == 64) return resident ? launch_v2<64, true>(prm, grid_x, n_tiles, smem, st) : launch_v2<64, false>(prm, grid_x, n_tiles, smem, st);
+    return resident ? launch_v2<128, true>(prm, grid_x, n_tiles, smem, st) : launch_v2<128, false>(prm, grid_x, n_tiles, smem, st);
+}
+
+
+// row-tile wgrad: returns TSB_ERR_UNSUPPORTED when the shape is not eligible (caller falls back to the patch kernel)
+int launch_wgrad_rows(const WgradDesc& d, cudaStream_t st) {
+    if (!g_allow_rows || d.Q < 64) return TSB_ERR_UNSUPPORTED;
+    WrParams prm;
+    memset(&prm, 0, sizeof(prm));
+    const int TW = 64;
+    int span_map[4] = {0, 0, 0, 0};
+    int ng = 0;
+    for (int t = 0; t < d.ntaps; ++t) {
+        const Tap& T = d.taps[t];
+        int g = -1;
+        for (int k = 0; k < ng; ++k) {
+            WrGroup& G = prm.groups[k];
+            if (G.map != T.map || G.dh != T.dh || G.ntaps >= 3) continue;
+            // taps arrive in increasing dw; keep a uniform step inside the group
+            int last = G.dw0 + (G.ntaps - 1) * G.step;
+            int step = T.dw - last;
+            if (step <= 0 || step > 4) continue;
+            if (G.ntaps == 1 || step == G.step) { g = k; if (G.ntaps == 1) G.step = step; break; }
+        }
+        if (g < 0) {
+            g = ng++;
+            prm.groups[g].map = T.map; prm.groups[g].dh = T.dh; prm.groups[g].dw0 = T.dw; prm.groups[g].ntaps = 0;
+            prm.groups[g].step = 1;
+        }
+        WrGroup& G = prm.groups[g];
+        G.tap_idx[G.ntaps++] = t;
+    }
+    for (int g = 0; g < ng; ++g) {
+        int span = (prm.groups[g].ntaps - 1) * prm.groups[g].step;
+        if (span > 8) return TSB_ERR_UNSUPPORTED;
+        if (span > span_map[prm.groups[g].map]) span_map[prm.groups[g].map] = span;
+    }
+    prm.ngroups = ng;
+    prm.cchunks = d.C / 64;
+    for (int m = 0; m < 4; ++m) prm.b_bytes[m] = (TW + span_map[m]) * 128;
+    int rc = encode_4d(&prm.mapA, d.dy, d.K, d.Q, d.P, d.N, (uint64_t)d.dycs * 2, (uint64_t)d.Q * d.dycs * 2,
+                       (uint64_t)d.P * d.Q * d.dycs * 2, 64, TW, 1, 1);
+    if (rc) return rc;
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(d.x);
+    if (d.stride == 1) {
+        rc = encode_4d(&prm.mapB[0], xb, d.C, d.W, d.H, d.N, (uint64_t)d.xcs * 2, (uint64_t)d.W * d.xcs * 2,
+                       (uint64_t)d.H * d.W * d.xcs * 2, 64, TW + span_map[0], 1, 1);
+        if (rc) return rc;
+    } else {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                int Hh = (d.H - ph + 1) / 2, Ww = (d.W - pw + 1) / 2;
+                if (Hh <= 0) Hh = 1;
+                if (Ww <= 0) Ww = 1;
+                rc = encode_4d(&prm.mapB[ph * 2 + pw], xb + ((long long)ph * d.W + pw) * d.xcs, d.C, Ww, Hh, d.N,
+                               (uint64_t)2 * d.xcs * 2, (uint64_t)2 * d.W * d.xcs * 2, (uint64_t)d.H * d.W * d.xcs * 2, 64,
+                               TW + span_map[ph * 2 + pw], 1, 1);
+                if (rc) return rc;
+            }
+    }
+    prm.TW = TW;
+    prm.tiles_w = (d.Q + TW - 1) / TW;
+    prm.tiles_h = d.P;
+    prm.total_tiles = prm.tiles_w * prm.tiles_h * d.N;
+    prm.K = d.K; prm.C = d.C; prm.dw_row_stride = d.dw_row_stride; prm.dw = d.dw;
+    const int co_tiles = (d.K + 127) / 128;
+    const int zdim = ng * prm.cchunks;
+    int base = zdim * co_tiles;
+    int want = (2 * tsb_num_sms() + base - 1) / base;
+    int max_splits = (prm.total_tiles + 15) / 16;
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    prm.tiles_per_split = (prm.total_tiles + want - 1) / want;
+    int splits = (prm.total_tiles + prm.tiles_per_split - 1) / prm.tiles_per_split;
+    static bool attr = false;
+    if (!attr) {
+        TSB_CUDA_CALL(cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWrSmem));
+        attr = true;
+    }
+    wgrad_rows_kernel<<<dim3(splits, co_tiles, zdim), 256, kWrSmem, st>>>(prm);
+    TSB_CUDA_CHECK_LAUNCH("wgrad_rows");
+    return TSB_OK;
+}
+
+}  // namespace convv2

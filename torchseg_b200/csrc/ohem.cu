@@ -446,17 +446,19 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
                     const float* __restrict__ cw, const uint32_t* __restrict__ state,
                     const float* __restrict__ gscale, float* __restrict__ dlo, int maxcols) {
     constexpr int kPitch = kStrip + 1;  // odd pitch → conflict-free column walks in phase 2
-    extern __shared__ float s_dyn[];    // s_g[CMAX][kPitch] then s_lo[2][maxcols][CMAX]
-    float (*s_g)[kPitch] = reinterpret_cast<float (*)[kPitch]>(s_dyn);
-    float* s_lo0 = s_dyn + CMAX * kPitch;
+    extern __shared__ float s_dyn[];    // s_g0[CMAX][kPitch], s_g1[CMAX][kPitch], s_lo[2][maxcols][CMAX]
+    float (*s_g0)[kPitch] = reinterpret_cast<float (*)[kPitch]>(s_dyn);
+    float (*s_g1)[kPitch] = reinterpret_cast<float (*)[kPitch]>(s_dyn + CMAX * kPitch);
+    float* s_lo0 = s_dyn + 2 * CMAX * kPitch;
     float* s_lo1 = s_lo0 + maxcols * CMAX;
     __shared__ float s_l0[kStrip], s_l1[kStrip];
-    __shared__ short s_j0[kStrip], s_j1[kStrip];
+    __shared__ short s_seg[kStrip + 8];  // s_seg[j] = first strip column whose left stencil column is >= j
     const bool active = state[ST_ACTIVE] != 0;
     const float Tth = __uint_as_float(state[ST_THRESH]);
     const float scale = __uint_as_float(state[ST_INVDEN]) * (gscale ? *gscale : 1.f);
     const float ry = area_scale(h, H), rx = area_scale(w, W);
     const int n = blockIdx.z, ci = blockIdx.y, x0 = blockIdx.x * kStrip, x1 = min(W, x0 + kStrip);
+    const int nx = x1 - x0;
     const int i1 = ci + (ci < h - 1 ? 1 : 0);
     const BandGeom g = band_geom(ry, rx, ci, x0, x1, H, w);
     if (g.ncols > maxcols) __trap();
@@ -468,87 +470,82 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
     const bool xin = x < x1;
     const Lerp lx = make_lerp(rx, xin ? x : x0, w);
     const int j0 = lx.i0 - g.jbase, j1 = lx.i1 - g.jbase;
-    s_j0[threadIdx.x] = xin ? (short)j0 : (short)-1;
-    s_j1[threadIdx.x] = xin ? (short)j1 : (short)-1;
-    s_l0[threadIdx.x] = lx.l0;
-    s_l1[threadIdx.x] = lx.l1;
-    // phase-2 ownership: pair q = j*C + c, up to 3 pairs per thread (ncols*C <= 72*19 would need more → loop)
-    constexpr int kMaxPairs = 6;  // host guarantees maxcols * C <= kMaxPairs * kThreads
-    float top[kMaxPairs], bot[kMaxPairs];
-#pragma unroll
-    for (int k = 0; k < kMaxPairs; ++k) { top[k] = 0.f; bot[k] = 0.f; }
-    const int npairs = g.ncols * C;
+    s_l0[threadIdx.x] = xin ? lx.l0 : 0.f;
+    s_l1[threadIdx.x] = xin ? lx.l1 : 0.f;
+    // segment starts: columns with left stencil index j form the contiguous range [s_seg[j], s_seg[j+1])
+    for (int q = threadIdx.x; q < g.ncols + 2; q += kThreads) s_seg[q] = (short)nx;
     __syncthreads();
+    if (xin) {
+        const int jprev = (threadIdx.x == 0) ? -1 : (make_lerp(rx, x - 1, w).i0 - g.jbase);
+        for (int jj = jprev + 1; jj <= j0; ++jj) s_seg[jj] = (short)threadIdx.x;
+    }
+    // ---- phase 1: per-thread accumulation over the rows of the band (registers only)
+    float G0[CMAX], G1[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) { G0[c] = 0.f; G1[c] = 0.f; }
     for (int y = g.y_lo; y <= g.y_hi; ++y) {
         const Lerp ly = make_lerp(ry, y, h);
-        if (ly.i0 != ci) continue;  // uniform across the CTA
-        // ---- phase 1
-        bool kept = false;
-        int t = 0;
-        float wt = 0.f;
-        if (xin) {
-            const long long pi = ((long long)n * H + y) * W + x;
-            long long lab = labels[pi];
-            kept = (lab != (long long)ignore_label) && (!active || p[pi] <= Tth);
-            t = kept ? (int)lab : 0;
-            if (kept) wt = (cw ? __ldg(cw + t) : 1.f) * scale;
-        }
-        if (kept) {
-            float v[CMAX];
-            float m = -INFINITY;
+        if (ly.i0 != ci || !xin) continue;
+        const long long pi = ((long long)n * H + y) * W + x;
+        const long long lab = labels[pi];
+        const bool kept = (lab != (long long)ignore_label) && (!active || p[pi] <= Tth);
+        if (!kept) continue;
+        const int t = (int)lab;
+        const float wt = (cw ? __ldg(cw + t) : 1.f) * scale;
+        float v[CMAX];
+        float m = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C) {
-                    v[c] = lerp4(ly, lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c], s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
-                    m = fmaxf(m, v[c]);
-                }
-            float ssum = 0.f;
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C) { v[c] = __expf(v[c] - m); ssum += v[c]; }
-            const float inv = wt / ssum;
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C) s_g[c][threadIdx.x] = v[c] * inv - (c == t ? wt : 0.f);
-        } else {
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C) s_g[c][threadIdx.x] = 0.f;
-        }
-        __syncthreads();
-        // ---- phase 2
-#pragma unroll
-        for (int k = 0; k < kMaxPairs; ++k) {
-            const int q = threadIdx.x + k * kThreads;
-            if (q < npairs) {
-                const int j = q / C, c = q - j * C;
-                // hi-res columns whose stencil touches low-res column jbase+j (one column of slack, exact re-check)
-                int xa, xb;
-                if (rx > 0.f) {
-                    xa = (int)floorf((float)(g.jbase + j - 1) / rx) - 1 - x0;
-                    xb = (int)ceilf((float)(g.jbase + j + 1) / rx) + 1 - x0;
-                } else { xa = 0; xb = kStrip - 1; }
-                xa = max(xa, 0);
-                xb = min(xb, x1 - x0 - 1);
-                float sacc = 0.f;
-                for (int xx = xa; xx <= xb; ++xx) {
-                    const float wgt = (s_j0[xx] == j ? s_l0[xx] : 0.f) + (s_j1[xx] == j ? s_l1[xx] : 0.f);
-                    sacc += wgt * s_g[c][xx];
-                }
-                top[k] += ly.l0 * sacc;
-                bot[k] += ly.l1 * sacc;
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) {
+                v[c] = lerp4(ly, lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c], s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
+                m = fmaxf(m, v[c]);
             }
-        }
-        __syncthreads();
+        float ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) { v[c] = __expf(v[c] - m); ssum += v[c]; }
+        const float inv = wt / ssum;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < C) {
+                const float gg = v[c] * inv - (c == t ? wt : 0.f);
+                G0[c] = fmaf(ly.l0, gg, G0[c]);
+                G1[c] = fmaf(ly.l1, gg, G1[c]);
+            }
     }
 #pragma unroll
-    for (int k = 0; k < kMaxPairs; ++k) {
-        const int q = threadIdx.x + k * kThreads;
-        if (q < npairs) {
-            const int j = q / C, c = q - j * C;
-            if (top[k] != 0.f) atomicAdd(dlo + (((long long)n * h + ci) * w + g.jbase + j) * cs + c, top[k]);
-            if (bot[k] != 0.f) atomicAdd(dlo + (((long long)n * h + i1) * w + g.jbase + j) * cs + c, bot[k]);
+    for (int c = 0; c < CMAX; ++c)
+        if (c < C) { s_g0[c][threadIdx.x] = G0[c]; s_g1[c][threadIdx.x] = G1[c]; }
+    __syncthreads();
+    // ---- phase 2 (once per band): low-res column j receives the l0x-weighted sum of its own segment and the
+    //      l1x-weighted sum of the previous segment (or of its own when the stencil is clamped at the last column)
+    const int npairs = g.ncols * C;
+    for (int q = threadIdx.x; q < npairs; q += kThreads) {
+        const int j = q / C, c = q - j * C;
+        const int a0 = s_seg[j], a1 = s_seg[j + 1];
+        float top = 0.f, bot = 0.f;
+        for (int xx = a0; xx < a1; ++xx) {
+            const float wl = s_l0[xx];
+            top = fmaf(wl, s_g0[c][xx], top);
+            bot = fmaf(wl, s_g1[c][xx], bot);
         }
+        const bool clamped = (g.jbase + j == w - 1);
+        const int b0 = clamped ? a0 : (j > 0 ? (int)s_seg[j - 1] : 0);
+        const int b1 = clamped ? a1 : (j > 0 ? a0 : 0);
+        for (int xx = b0; xx < b1; ++xx) {
+            const float wr = s_l1[xx];
+            top = fmaf(wr, s_g0[c][xx], top);
+            bot = fmaf(wr, s_g1[c][xx], bot);
+        }
+        if (clamped && j > 0) {  // the previous segment still points at this (last) column with its right weight
+            for (int xx = s_seg[j - 1]; xx < a0; ++xx) {
+                const float wr = s_l1[xx];
+                top = fmaf(wr, s_g0[c][xx], top);
+                bot = fmaf(wr, s_g1[c][xx], bot);
+            }
+        }
+        if (top != 0.f) atomicAdd(dlo + (((long long)n * h + ci) * w + g.jbase + j) * cs + c, top);
+        if (bot != 0.f) atomicAdd(dlo + (((long long)n * h + i1) * w + g.jbase + j) * cs + c, bot);
     }
 }
 
@@ -672,8 +669,8 @@ extern "C" int tsb_ohem_grad_up(const float* logits_lo, int cs, int h, int w, co
     TSB_REQUIRE(N <= 65535 && h <= 65535, "tsb_ohem_grad_up: N and h must fit a grid dimension");
     const int maxcols = band_maxcols(w, W);
     const int cmax = C <= 20 ? 20 : 32;
-    TSB_REQUIRE(maxcols * C <= 6 * kThreads, "tsb_ohem_grad_up: up-scale factor W/w too small for the band kernel");
-    const size_t smem = sizeof(float) * ((size_t)cmax * (kStrip + 1) + 2 * (size_t)maxcols * cmax);
+    TSB_REQUIRE(maxcols <= kStrip, "tsb_ohem_grad_up: up-scale factor W/w too small for the band kernel");
+    const size_t smem = sizeof(float) * (2 * (size_t)cmax * (kStrip + 1) + 2 * (size_t)maxcols * cmax);
     TSB_REQUIRE(smem <= 96 * 1024, "tsb_ohem_grad_up: shared memory budget exceeded");
     dim3 grid((W + kStrip - 1) / kStrip, h, N);
     cudaStream_t st = (cudaStream_t)stream;
