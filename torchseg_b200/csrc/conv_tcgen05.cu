@@ -314,22 +314,25 @@ __global__ void __launch_bounds__(kThreadsConv, 1) wgrad_mnmajor_kernel(const __
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64 * nb, true, true);
+            // MN-major, SWIZZLE_128B: 64-channel groups are LBO = 8192 B apart (one TMA box each), 8-pixel groups
+            // SBO = 1024 B apart; one MMA consumes 16 pixels = 2048 B = 128 descriptor units
+            const uint64_t d_hi = make_smem_desc_sw128(0, kWgBoxBytes, 1024);
+            const uint32_t base_lo = smem_u32(smem) >> 4;
+            int s = 0;
+            uint32_t ph = 0, acc = 0;
             for (int it = 0; it < total_iters; ++it) {
-                const int s = it % kWgStages;
-                const uint32_t ph = (uint32_t)(it / kWgStages) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * kWgStageBytes);
-                const uint32_t b_addr = a_addr + 2 * kWgBoxBytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // MN-major, SWIZZLE_128B: 64-channel groups are LBO = 8192 B apart (one TMA box each),
-                    // 8-pixel groups SBO = 1024 B apart; one MMA consumes 16 pixels = 2048 B
-                    uint64_t da = make_smem_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
-                    uint64_t db = make_smem_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-                }
+                const uint32_t a_lo = base_lo + (uint32_t)(s * (kWgStageBytes >> 4));
+                const uint64_t da = d_hi | (uint64_t)a_lo;
+                const uint64_t db = d_hi | (uint64_t)(a_lo + ((2 * kWgBoxBytes) >> 4));
+                umma_bf16(tmem_base, da, db, idesc, acc);
+                umma_bf16(tmem_base, da + 128, db + 128, idesc, 1u);
+                umma_bf16(tmem_base, da + 256, db + 256, idesc, 1u);
+                umma_bf16(tmem_base, da + 384, db + 384, idesc, 1u);
+                acc = 1u;
                 umma_commit(&empty_bar[s]);
+                if (++s == kWgStages) { s = 0; ph ^= 1u; }
             }
             if (total_iters > 0) umma_commit(tmem_full);
         }

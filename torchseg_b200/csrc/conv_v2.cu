@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
     uint64_t* b_ready = tmem_empty + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_ready + 1);
     float* s_stats = reinterpret_cast<float*>(tail + 256);  // [2*BN]
+    uint32_t* s_tr = reinterpret_cast<uint32_t*>(tail + 256 + 2 * BN * 4);  // [8 warps][32][17] bf16x2 transposition
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
@@ -78,7 +79,6 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
         fence_barrier_init();
     } else if (warp == 2) {
         tmem_alloc<2 * BN>(tmem_ptr);
-    } else if (warp == 3) {
         for (int i = lane; i < 2 * BN; i += 32) s_stats[i] = 0.f;
     }
     tc_fence_before();
@@ -96,65 +96,90 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                             tma_load_2d(res_b + (p.groups[g].tap_idx[t] * p.kchunks + kc) * kBTile, &p.mapB, b_ready,
                                         p.groups[g].bk[t] + kc * 64, n0);
             }
-            int it = 0;
+            // two stage rings (one per MMA-issuing thread) when there are >= 4 stages: tile i uses ring i & 1
+            const bool dual_p = p.nstages >= 4;
+            const int half_p = dual_p ? p.nstages / 2 : p.nstages;
+            int cs0 = 0, cs1 = 0;
+            uint32_t cp0 = 0, cp1 = 0;
             for (int i = 0; i < my_tiles; ++i) {
+                const bool r1 = dual_p && (i & 1);
+                int sl = r1 ? cs1 : cs0;
+                uint32_t ph = r1 ? cp1 : cp0;
+                const int sbase = r1 ? half_p : 0;
                 const int tile = blockIdx.x + i * gridDim.x;
                 const int tw_i = tile % p.tiles_w;
                 const int th_i = (tile / p.tiles_w) % p.tiles_h;
                 const int n_img = tile / (p.tiles_w * p.tiles_h);
                 const int q0 = tw_i * p.TW, p0 = th_i * p.TH;
                 for (int g = 0; g < p.ngroups; ++g) {
-                    const TapGroup G = p.groups[g];
-                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-                        const int s = it % p.nstages;
-                        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                    const int gmap = p.groups[g].map, ntaps = p.groups[g].ntaps;
+                    const int cw = q0 + p.groups[g].dw0, chh = p0 + p.groups[g].dh;
+                    const uint32_t bytes = (uint32_t)p.a_bytes[gmap] + (RES ? 0u : (uint32_t)(ntaps * kBTile));
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        const int s = sbase + sl;
                         mbar_wait(&empty_bar[s], ph ^ 1u);
                         uint8_t* a_s = stages + s * p.stage_bytes;
-                        const uint32_t bytes = (uint32_t)p.a_bytes[G.map] + (RES ? 0u : (uint32_t)(G.ntaps * kBTile));
                         mbar_arrive_expect_tx(&full_bar[s], bytes);
-                        tma_load_4d(a_s, &p.mapA[G.map], &full_bar[s], kc * 64, q0 + G.dw0, p0 + G.dh, n_img);
+                        tma_load_4d(a_s, &p.mapA[gmap], &full_bar[s], kc * 64, cw, chh, n_img);
                         if (!RES) {
-                            for (int t = 0; t < G.ntaps; ++t)
-                                tma_load_2d(a_s + kAStageBytes + t * kBTile, &p.mapB, &full_bar[s], G.bk[t] + kc * 64, n0);
+                            for (int t = 0; t < ntaps; ++t)
+                                tma_load_2d(a_s + kAStageBytes + t * kBTile, &p.mapB, &full_bar[s], p.groups[g].bk[t] + kc * 64, n0);
                         }
+                        if (++sl == half_p) { sl = 0; ph ^= 1u; }
                     }
                 }
+                if (r1) { cs1 = sl; cp1 = ph; } else { cs0 = sl; cp0 = ph; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0 && my_tiles > 0) {
+    } else if (warp == 1 || warp == 3) {
+        // TWO MMA-issuing threads (one elected lane each): warp 1 takes the even local tiles (TMEM buffer 0), warp 3
+        // the odd ones (buffer 1). A single thread cannot issue N=64 MMAs fast enough to keep the tensor pipe busy;
+        // the per-MMA work is reduced to two 64-bit descriptor adds.
+        // Each issuing thread owns its own stage ring (single producer / single consumer per ring), so the mbarrier
+        // parity waits can never alias an older phase whatever the K-loop length. With < 4 stages warp 1 works alone.
+        const bool dual = p.nstages >= 4;
+        const int half = dual ? p.nstages / 2 : p.nstages;
+        const int par = (warp == 3) ? 1 : 0;
+        const int tstep = dual ? 2 : 1;
+        if (lane == 0 && my_tiles > par && (dual || warp == 1)) {
             constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, false);
+            // descriptor with a zero start address: LBO = 16 B, SBO = 1024 B, version 1, SWIZZLE_128B
+            const uint64_t desc_hi = make_smem_desc_sw128(0, 16, 1024);
+            const uint32_t stages_u32 = smem_u32(stages);
+            const uint32_t res_u32 = smem_u32(res_b);
             if (RES) { mbar_wait(b_ready, 0); tc_fence_after(); }
-            int it = 0;
-            for (int i = 0; i < my_tiles; ++i) {
+            const int sbase = (dual && par) ? half : 0;
+            int sl = 0;
+            uint32_t ph = 0;
+            for (int i = par; i < my_tiles; i += tstep) {
                 const int buf = i & 1;
                 mbar_wait(&tmem_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * BN;
-                uint32_t first = 1;
+                uint32_t acc = 0;
                 for (int g = 0; g < p.ngroups; ++g) {
-                    const TapGroup G = p.groups[g];
-                    for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-                        const int s = it % p.nstages;
-                        const uint32_t ph = (uint32_t)(it / p.nstages) & 1u;
+                    const int ntaps = p.groups[g].ntaps;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        const int s = sbase + sl;
                         mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
-                        const uint32_t a_base = smem_u32(stages + s * p.stage_bytes);
-                        for (int t = 0; t < G.ntaps; ++t) {
-                            const uint32_t a_addr = a_base + G.row_off[t] * 128;
-                            const uint32_t b_addr = RES ? smem_u32(res_b + (G.tap_idx[t] * p.kchunks + kc) * kBTile)
-                                                        : a_base + kAStageBytes + t * kBTile;
-                            // start shifted by whole 128-byte rows: swizzle phase carried in base_offset
-                            const uint64_t bo = p.use_base_offset ? ((uint64_t)((a_addr >> 7) & 7u) << 49) : 0ull;
+                        const uint32_t a_lo = (stages_u32 + (uint32_t)(s * p.stage_bytes)) >> 4;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024) | bo;
-                                uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                                umma_bf16(d_tmem, da, db, idesc, first ? 0u : 1u);
-                                first = 0;
+                        for (int t = 0; t < 3; ++t) {
+                            if (t < ntaps) {
+                                const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)p.groups[g].row_off[t] * 8u);
+                                const uint32_t b_lo = RES ? (res_u32 + (uint32_t)((p.groups[g].tap_idx[t] * p.kchunks + kc) * kBTile)) >> 4
+                                                          : a_lo + (uint32_t)((kAStageBytes + t * kBTile) >> 4);
+                                const uint64_t db = desc_hi | (uint64_t)b_lo;
+                                umma_bf16(d_tmem, da, db, idesc, acc);
+                                umma_bf16(d_tmem, da + 2, db + 2, idesc, 1u);
+                                umma_bf16(d_tmem, da + 4, db + 4, idesc, 1u);
+                                umma_bf16(d_tmem, da + 6, db + 6, idesc, 1u);
+                                acc = 1u;
                             }
                         }
                         umma_commit(&empty_bar[s]);
+                        if (++sl == half) { sl = 0; ph ^= 1u; }
                     }
                 }
                 umma_commit(&tmem_full[buf]);
@@ -171,9 +196,9 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
         const bool do_stats = (p.sum != nullptr);
         constexpr bool kRunning = (BN == 64);
         constexpr int kChunksPerWarp = kRunning ? 1 : 2;
-        float run1[kRunning ? 32 : 1], run2[kRunning ? 32 : 1];
+        float run1[kRunning ? 32 : 2], run2[kRunning ? 32 : 2];
 #pragma unroll
-        for (int q = 0; q < (kRunning ? 32 : 1); ++q) { run1[q] = 0.f; run2[q] = 0.f; }
+        for (int q = 0; q < (kRunning ? 32 : 2); ++q) { run1[q] = 0.f; run2[q] = 0.f; }
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int tw_i = tile % p.tiles_w;
@@ -250,24 +275,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                             for (int q = 0; q < 32; ++q) { run1[q] += v[q]; run2[q] = fmaf(v[q], v[q], run2[q]); }
                         }
                     } else {
-                        float s1[32], s2[32];
+                        // column sums through a bf16x2 shared-memory transposition (conflict-free: pitch 17 words);
+                        // lane c then owns column c and keeps running sums over all tiles of the CTA
+                        uint32_t* tr = s_tr + (warp - 4) * (32 * 17);
+                        __syncwarp();
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) { s1[q] = valid ? v[q] : 0.f; s2[q] = s1[q] * s1[q]; }
+                        for (int q = 0; q < 16; ++q) tr[lane * 17 + q] = valid ? pack_bf16(v[2 * q], v[2 * q + 1]) : 0u;
+                        __syncwarp();
+                        float a1 = 0.f, a2 = 0.f;
+                        const int wq = lane >> 1;
+                        const bool hi = (lane & 1) != 0;
 #pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1) {
-                            const bool upper = (lane & off) != 0;
-#pragma unroll
-                            for (int q = 0; q < off; ++q) {
-                                float send1 = upper ? s1[q] : s1[q + off];
-                                float keep1 = upper ? s1[q + off] : s1[q];
-                                float send2 = upper ? s2[q] : s2[q + off];
-                                float keep2 = upper ? s2[q + off] : s2[q];
-                                s1[q] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-                                s2[q] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-                            }
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const uint32_t u = tr[rr * 17 + wq];
+                            const float f = hi ? bf16hi(u) : bf16lo(u);
+                            a1 += f;
+                            a2 = fmaf(f, f, a2);
                         }
-                        atomicAdd(&s_stats[j * 32 + lane], s1[0]);
-                        atomicAdd(&s_stats[BN + j * 32 + lane], s2[0]);
+                        run1[jj] += a1;
+                        run2[jj] += a2;
                     }
                 }
             }
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                 for (int off = 16; off >= 1; off >>= 1) {
                     const bool upper = (lane & off) != 0;
 #pragma unroll
-                    for (int q = 0; q < off; ++q) {
+                    for (int q = 0; q < (kRunning ? off : 0); ++q) {
                         float send1 = upper ? run1[q] : run1[q + off];
                         float keep1 = upper ? run1[q + off] : run1[q];
                         float send2 = upper ? run2[q] : run2[q + off];
@@ -289,6 +315,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                 }
                 atomicAdd(&s_stats[chalf * 32 + lane], run1[0]);
                 atomicAdd(&s_stats[BN + chalf * 32 + lane], run2[0]);
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    atomicAdd(&s_stats[(chalf * 2 + jj) * 32 + lane], run1[jj]);
+                    atomicAdd(&s_stats[BN + (chalf * 2 + jj) * 32 + lane], run2[jj]);
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
             for (int i = threadIdx.x - 128; i < BN; i += 256) {
@@ -385,20 +417,25 @@ __global__ void __launch_bounds__(256, 1) wgrad_rows_kernel(const __grid_constan
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64 * G.ntaps, true, true);
             const uint32_t b_lbo = (uint32_t)(G.ntaps > 1 ? G.step * 128 : 128);
+            const uint64_t da_hi = make_smem_desc_sw128(0, 64 * 128, 1024);
+            const uint64_t db_hi = make_smem_desc_sw128(0, b_lbo, 1024);
+            const uint32_t base_lo = smem_u32(smem) >> 4;
+            int s = 0;
+            uint32_t ph = 0, acc = 0;
             for (int it = 0; it < total_iters; ++it) {
-                const int s = it % kWrStages;
-                const uint32_t ph = (uint32_t)(it / kWrStages) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * kWrStageBytes);
-                const uint32_t b_addr = a_addr + kWrABytes;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint64_t da = make_smem_desc_sw128(a_addr + k * 2048, 64 * 128, 1024);
-                    uint64_t db = make_smem_desc_sw128(b_addr + k * 2048, b_lbo, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-                }
+                const uint32_t a_lo = base_lo + (uint32_t)(s * (kWrStageBytes >> 4));
+                const uint64_t da = da_hi | (uint64_t)a_lo;
+                const uint64_t db = db_hi | (uint64_t)(a_lo + (kWrABytes >> 4));
+                // one MMA consumes 16 pixels = 2048 B = 128 descriptor units
+                umma_bf16(tmem_base, da, db, idesc, acc);
+                umma_bf16(tmem_base, da + 128, db + 128, idesc, 1u);
+                umma_bf16(tmem_base, da + 256, db + 256, idesc, 1u);
+                umma_bf16(tmem_base, da + 384, db + 384, idesc, 1u);
+                acc = 1u;
                 umma_commit(&empty_bar[s]);
+                if (++s == kWrStages) { s = 0; ph ^= 1u; }
             }
             if (total_iters > 0) umma_commit(tmem_full);
         }
@@ -549,7 +586,7 @@ int launch(const Desc& d, cudaStream_t st) {
     const int kBTile = BN * 128;
     const long long res_need = (long long)d.ntaps * d.kchunks * kBTile;
     const bool resident = g_allow_resident && res_need <= 112 * 1024 && prm.m_tiles > 0;
-    const int tail = 256 + 2 * BN * 4;
+    const int tail = 256 + 2 * BN * 4 + 8 * 32 * 17 * 4;
     const int budget = 227 * 1024 - 1024 /*align*/ - tail;
     int max_group_taps = 1;
     for (int g = 0; g < ng; ++g) if (prm.groups[g].ntaps > max_group_taps) max_group_taps = prm.groups[g].ntaps;

@@ -196,7 +196,11 @@ def conv_dgrad(dy, wt, xshape, K, R, stride, pad, dil, out=None, accumulate=Fals
     if out is None:
         out = nhwc_empty(N, C, H, W, device=dy.device)
     ev = conv_prof.begin()
-    call("tsb_conv2d_dgrad", ctypes.byref(shp), ptr(dy), cs_of(dy), ptr(wt), ptr(out), cs_of(out), int(accumulate), stream())
+    try:
+        call("tsb_conv2d_dgrad", ctypes.byref(shp), ptr(dy), cs_of(dy), ptr(wt), ptr(out), cs_of(out), int(accumulate), stream())
+    except RuntimeError as e:
+        raise RuntimeError("%s [dgrad shape N=%d H=%d W=%d C=%d K=%d R=%d stride=%d pad=%d dil=%d]" % (
+            e, N, H, W, C, K, R, stride, pad, dil)) from None
     conv_prof.end(ev, _conv_flops(shp))
     return out
 
