@@ -150,14 +150,19 @@ int tsb_bn_finalize(const float* sum, const float* sumsq, double count, int C, c
 /* y = act(x*scale[c] + shift[c] + residual); act = ReLU if relu. x,y,residual bf16 NHWC (own strides) */
 int tsb_bn_apply(const void* x, int xcs, const float* scale, const float* shift, const void* residual, int rcs,
                  int relu, void* y, int ycs, long long npix, int C, tsb_stream_t stream);
-/* backward pass 1: dz = dy * (relu ? y>0 : 1); sum_dz[c] += Σ dz ; sum_dz_xhat[c] += Σ dz * (x-mean)*invstd */
+/* backward pass 1: dz = dy * (relu ? y>0 : 1); sum_dz[c] += Σ dz ; sum_dz_xhat[c] += Σ dz * (x-mean)*invstd.
+ * With relu and y == NULL the mask is recomputed as fma(x, scale[c], shift[c]) > 0 (exact for layers WITHOUT a
+ * residual input) and the read of y is saved; scale/shift are then required. */
 int tsb_bn_bwd_reduce(const void* dy, int dycs, const void* y, int ycs, const void* x, int xcs, const float* mean,
                       const float* invstd, int relu, long long npix, int C, float* sum_dz, float* sum_dz_xhat,
-                      tsb_stream_t stream);
-/* backward pass 2: dx = gamma*invstd*(dz - sum_dz/cnt - xhat*sum_dz_xhat/cnt); optional dres = dz */
+                      const float* scale, const float* shift, tsb_stream_t stream);
+/* backward pass 2: dx = gamma*invstd*(dz - sum_dz/cnt - xhat*sum_dz_xhat/cnt); optional dres = dz;
+ * optional dgamma_acc[c] += sum_dz_xhat[c], dbeta_acc[c] += sum_dz[c] (parameter gradients, folded into this pass);
+ * y == NULL with relu: mask recomputed from scale/shift as in tsb_bn_bwd_reduce */
 int tsb_bn_bwd_apply(const void* dy, int dycs, const void* y, int ycs, const void* x, int xcs, const float* mean,
                      const float* invstd, const float* gamma, const float* sum_dz, const float* sum_dz_xhat,
                      double count, int relu, void* dx, int dxcs, void* dres, int drcs, long long npix, int C,
+                     float* dgamma_acc, float* dbeta_acc, const float* scale, const float* shift,
                      tsb_stream_t stream);
 
 /* ================================================================================================

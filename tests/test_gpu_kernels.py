@@ -245,12 +245,14 @@ def test_bn_kernels(cuda, relu, res):
     assert rel_err(yd, yr) < 1e-2
     assert rel_err(rmd, rm) < 1e-3 and rel_err(rvd, rv) < 1e-3
     red = torch.zeros(2, C, device=cuda)
-    ops.call("tsb_bn_bwd_reduce", ops.ptr(gyd), C, ops.ptr(yd), C, ops.ptr(xd), C, ops.ptr(aux[0]), ops.ptr(aux[1]),
-             int(relu), npix, C, ops.ptr(red[0]), ops.ptr(red[1]), ops.stream())
+    # residual layers read the mask from y; the others recompute it from x*scale+shift (y = NULL)
+    ymask = ops.ptr(yd) if (relu and res) else None
+    ops.call("tsb_bn_bwd_reduce", ops.ptr(gyd), C, ymask, C, ops.ptr(xd), C, ops.ptr(aux[0]), ops.ptr(aux[1]),
+             int(relu), npix, C, ops.ptr(red[0]), ops.ptr(red[1]), ops.ptr(aux[2]), ops.ptr(aux[3]), ops.stream())
     dx = ops.nhwc_empty(N, C, H, W); dres = ops.nhwc_empty(N, C, H, W)
-    ops.call("tsb_bn_bwd_apply", ops.ptr(gyd), C, ops.ptr(yd), C, ops.ptr(xd), C, ops.ptr(aux[0]), ops.ptr(aux[1]),
+    ops.call("tsb_bn_bwd_apply", ops.ptr(gyd), C, ymask, C, ops.ptr(xd), C, ops.ptr(aux[0]), ops.ptr(aux[1]),
              ops.ptr(gam), ops.ptr(red[0]), ops.ptr(red[1]), float(npix), int(relu), ops.ptr(dx), C,
-             ops.ptr(dres) if res else None, C, npix, C, ops.stream())
+             ops.ptr(dres) if res else None, C, npix, C, None, None, ops.ptr(aux[2]), ops.ptr(aux[3]), ops.stream())
     assert rel_err(dx, xr.grad) < 2e-2
     assert rel_err(red[1], gr.grad) < 1e-2 and rel_err(red[0], br.grad) < 1e-2
     if res:

@@ -72,8 +72,13 @@ class DistributedDataParallel(nn.Module):
                     dist.broadcast(p.data, 0)
                 for b in module.buffers():
                     dist.broadcast(b.data, 0)
+            hooks = {}
             for i, p in enumerate(params):
-                p.register_post_accumulate_grad_hook(self._make_hook(i))
+                h = self._make_hook(i)
+                hooks[id(p)] = h
+                p.register_post_accumulate_grad_hook(h)
+            # gradients written straight into the flat views by the kernels bypass AccumulateGrad: same bucket logic
+            ops.grad_ready_hook = lambda prm: hooks[id(prm)](prm) if id(prm) in hooks else None
 
     def _make_hook(self, idx):
         def hook(param):
@@ -110,6 +115,7 @@ class DistributedDataParallel(nn.Module):
     def zero_grad(self, set_to_none=False):
         ensure_flat_grads(self._params)
         self.flat_grad.zero_()
+        ops.zero_arena.reset()
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)

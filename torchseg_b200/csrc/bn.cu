@@ -80,19 +80,31 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     }
 }
 
+// Elementwise kernels below are launched with gridDim.x*kThreads a multiple of C8 whenever C8 divides kThreads
+// (all power-of-two channel counts): a thread then keeps the SAME 8-channel group for its whole grid-stride loop and
+// the per-channel parameters are loaded into registers once (otherwise the LSU, not HBM, bounds the kernel).
 template <bool kRelu, bool kRes>
 __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int rcs,
                 __nv_bfloat16* __restrict__ y, int ycs, long long npix, int C8) {
     const long long total = npix * C8;
+    const bool hoist = (kThreads % C8) == 0;
+    float sc[8], sh[8];
+    if (hoist) {
+        const int c8 = threadIdx.x % C8;
+        ldg8f(scale + c8 * 8, sc);
+        ldg8f(shift + c8 * 8, sh);
+    }
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
         int c8 = (int)(i % C8);
         long long p = i / C8;
-        float v[8], sc[8], sh[8];
+        float v[8];
         Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, v);
-        ldg8f(scale + c8 * 8, sc);
-        ldg8f(shift + c8 * 8, sh);
+        if (!hoist) {
+            ldg8f(scale + c8 * 8, sc);
+            ldg8f(shift + c8 * 8, sh);
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
         if (kRes) {
@@ -109,60 +121,124 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const float* __res
     }
 }
 
-template <bool kRelu>
+// kRelu: 0 = no activation, 1 = ReLU mask read from y (y > 0), 2 = mask recomputed as fma(x, scale, shift) > 0 —
+// exact for layers without a residual (bf16 rounding keeps the sign), and saves the whole read of y.
+template <int kRelu>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ y, int ycs,
                      const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, long long npix, int C8, float* sum_dz, float* sum_dz_xhat) {
-    float* const outs[2] = {sum_dz, sum_dz_xhat};
-    column_reduce<2>(npix, C8, outs, [&](long long p, int cg, float (&acc)[2][8]) {
-        float g[8], xv[8], m[8], is[8];
-        Vec8<__nv_bfloat16>::load(dy + p * dycs + cg * 8, g);
-        Vec8<__nv_bfloat16>::load(x + p * xcs + cg * 8, xv);
-        ldg8f(mean + cg * 8, m);
-        ldg8f(invstd + cg * 8, is);
-        if (kRelu) {
-            float yv[8];
-            Vec8<__nv_bfloat16>::load(y + p * ycs + cg * 8, yv);
+                     const float* __restrict__ invstd, const float* __restrict__ scale, const float* __restrict__ shift,
+                     long long npix, int C8, float* sum_dz, float* sum_dz_xhat) {
+    // inner loop: acc0 += dz, acc1 += dz*x (no per-pixel parameter loads); Σ dz·x̂ = invstd·(acc1 − mean·acc0) is
+    // formed once per (block, channel) when the partial sums are flushed.
+    extern __shared__ float s_buf[];  // [lanes][groups][2][8]
+    const int groups = min(C8, kThreads);
+    const int lanes = kThreads / groups;
+    const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+    const long long chunk = (npix + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * chunk;
+    const long long p1 = (p0 + chunk < npix) ? p0 + chunk : npix;
+    for (int g0 = 0; g0 < C8; g0 += groups) {
+        const int cg = g0 + g;
+        float a0[8], a1[8], sc[8], sh[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
+        for (int k = 0; k < 8; ++k) { a0[k] = 0.f; a1[k] = 0.f; sc[k] = 0.f; sh[k] = 0.f; }
+        if (cg < C8 && lane < lanes) {
+            if (kRelu == 2) { ldg8f(scale + cg * 8, sc); ldg8f(shift + cg * 8, sh); }
+            for (long long pp = p0 + lane; pp < p1; pp += lanes) {
+                float gv[8], xv[8];
+                Vec8<__nv_bfloat16>::load(dy + pp * dycs + cg * 8, gv);
+                Vec8<__nv_bfloat16>::load(x + pp * xcs + cg * 8, xv);
+                if (kRelu == 1) {
+                    float yv[8];
+                    Vec8<__nv_bfloat16>::load(y + pp * ycs + cg * 8, yv);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) gv[k] = yv[k] > 0.f ? gv[k] : 0.f;
+                } else if (kRelu == 2) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) gv[k] = fmaf(xv[k], sc[k], sh[k]) > 0.f ? gv[k] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { a0[k] += gv[k]; a1[k] = fmaf(gv[k], xv[k], a1[k]); }
+            }
         }
+        if (lane < lanes) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { acc[0][k] += g[k]; acc[1][k] += g[k] * (xv[k] - m[k]) * is[k]; }
-    });
+            for (int k = 0; k < 8; ++k) {
+                s_buf[((lane * groups + g) * 2 + 0) * 8 + k] = a0[k];
+                s_buf[((lane * groups + g) * 2 + 1) * 8 + k] = a1[k];
+            }
+        }
+        __syncthreads();
+        if (cg < C8 && lane < lanes) {
+            for (int k = lane; k < 8; k += lanes) {
+                float t0 = 0.f, t1 = 0.f;
+                for (int l = 0; l < lanes; ++l) {
+                    t0 += s_buf[((l * groups + g) * 2 + 0) * 8 + k];
+                    t1 += s_buf[((l * groups + g) * 2 + 1) * 8 + k];
+                }
+                const int c = cg * 8 + k;
+                atomicAdd(sum_dz + c, t0);
+                atomicAdd(sum_dz_xhat + c, __ldg(invstd + c) * (t1 - __ldg(mean + c) * t0));
+            }
+        }
+        __syncthreads();
+    }
 }
 
-template <bool kRelu, bool kDres>
+template <int kRelu, bool kDres>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ y, int ycs,
                     const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ sum_dz, const float* __restrict__ sum_dz_xhat, float inv_count,
                     __nv_bfloat16* __restrict__ dx, int dxcs, __nv_bfloat16* __restrict__ dres, int drcs,
-                    long long npix, int C8) {
+                    long long npix, int C8, float* dgamma_acc, float* dbeta_acc, const float* __restrict__ scale,
+                    const float* __restrict__ shift) {
+    if (dgamma_acc != nullptr && blockIdx.x == 0) {  // fold the parameter-gradient accumulation into this pass
+        for (int c = threadIdx.x; c < C8 * 8; c += kThreads) {
+            dgamma_acc[c] += sum_dz_xhat[c];
+            dbeta_acc[c] += sum_dz[c];
+        }
+    }
+    // dx = γ·σ⁻¹·(dz − Σdz/n − x̂·Σdz·x̂/n), x̂ = (x−μ)σ⁻¹   ⇒   dx = A·dz + B·x + C  with per-channel
+    //   A = γσ⁻¹,  B = −γσ⁻²·Σdz·x̂/n,  C = −A·Σdz/n − B·μ
+    auto coeffs = [&](int c8, float (&A)[8], float (&B)[8], float (&Cc)[8], float (&sc)[8], float (&sh)[8]) {
+        float m[8], is[8], ga[8], s1[8], s2[8];
+        ldg8f(mean + c8 * 8, m); ldg8f(invstd + c8 * 8, is); ldg8f(gamma + c8 * 8, ga);
+        ldg8f(sum_dz + c8 * 8, s1); ldg8f(sum_dz_xhat + c8 * 8, s2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            A[k] = ga[k] * is[k];
+            B[k] = -A[k] * is[k] * s2[k] * inv_count;
+            Cc[k] = -A[k] * s1[k] * inv_count - B[k] * m[k];
+        }
+        if (kRelu == 2) { ldg8f(scale + c8 * 8, sc); ldg8f(shift + c8 * 8, sh); }
+    };
     const long long total = npix * C8;
+    const bool hoist = (kThreads % C8) == 0;
+    float A[8], B[8], Cc[8], sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sc[k] = 0.f; sh[k] = 0.f; }
+    if (hoist) coeffs(threadIdx.x % C8, A, B, Cc, sc, sh);
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
         int c8 = (int)(i % C8);
         long long p = i / C8;
-        float g[8], xv[8], m[8], is[8], ga[8], s1[8], s2[8], o[8];
+        if (!hoist) coeffs(c8, A, B, Cc, sc, sh);
+        float g[8], xv[8], o[8];
         Vec8<__nv_bfloat16>::load(dy + p * dycs + c8 * 8, g);
         Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, xv);
-        ldg8f(mean + c8 * 8, m);
-        ldg8f(invstd + c8 * 8, is);
-        ldg8f(gamma + c8 * 8, ga);
-        ldg8f(sum_dz + c8 * 8, s1);
-        ldg8f(sum_dz_xhat + c8 * 8, s2);
-        if (kRelu) {
+        if (kRelu == 1) {
             float yv[8];
             Vec8<__nv_bfloat16>::load(y + p * ycs + c8 * 8, yv);
 #pragma unroll
             for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
+        } else if (kRelu == 2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = fmaf(xv[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float xhat = (xv[k] - m[k]) * is[k];
-            o[k] = ga[k] * is[k] * (g[k] - s1[k] * inv_count - xhat * s2[k] * inv_count);
-        }
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], g[k], fmaf(B[k], xv[k], Cc[k]));
         Vec8<__nv_bfloat16>::store(dx + p * dxcs + c8 * 8, o);
         if (kDres) Vec8<__nv_bfloat16>::store(dres + p * drcs + c8 * 8, g);
     }
@@ -300,15 +376,16 @@ extern "C" int tsb_bn_apply(const void* x, int xcs, const float* scale, const fl
 
 extern "C" int tsb_bn_bwd_reduce(const void* dy, int dycs, const void* y, int ycs, const void* x, int xcs,
                                  const float* mean, const float* invstd, int relu, long long npix, int C, float* sum_dz,
-                                 float* sum_dz_xhat, tsb_stream_t stream) {
-    TSB_REQUIRE(dy && x && mean && invstd && sum_dz && sum_dz_xhat && npix > 0 && (!relu || y), "tsb_bn_bwd_reduce: bad args");
-    TSB_REQUIRE(TSB_VEC_OK(C, dycs, dy) && TSB_VEC_OK(C, xcs, x) && (!relu || TSB_VEC_OK(C, ycs, y)), "tsb_bn_bwd_reduce: alignment");
+                                 float* sum_dz_xhat, const float* scale, const float* shift, tsb_stream_t stream) {
+    TSB_REQUIRE(dy && x && mean && invstd && sum_dz && sum_dz_xhat && npix > 0, "tsb_bn_bwd_reduce: bad args");
+    const int mode = !relu ? 0 : (y ? 1 : 2);
+    TSB_REQUIRE(mode != 2 || (scale && shift), "tsb_bn_bwd_reduce: relu without y needs scale and shift");
+    TSB_REQUIRE(TSB_VEC_OK(C, dycs, dy) && TSB_VEC_OK(C, xcs, x) && (mode != 1 || TSB_VEC_OK(C, ycs, y)), "tsb_bn_bwd_reduce: alignment");
     int C8 = C / 8;
     cudaStream_t st = (cudaStream_t)stream;
-    if (relu)
-        bn_bwd_reduce_kernel<true><<<colred_grid(npix, C8), kThreads, colred_smem(C8, 2), st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, npix, C8, sum_dz, sum_dz_xhat);
-    else
-        bn_bwd_reduce_kernel<false><<<colred_grid(npix, C8), kThreads, colred_smem(C8, 2), st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, npix, C8, sum_dz, sum_dz_xhat);
+#define L(M) bn_bwd_reduce_kernel<M><<<colred_grid(npix, C8), kThreads, colred_smem(C8, 2), st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, scale, shift, npix, C8, sum_dz, sum_dz_xhat)
+    if (mode == 0) L(0); else if (mode == 1) L(1); else L(2);
+#undef L
     TSB_CUDA_CHECK_LAUNCH("bn_bwd_reduce");
     return TSB_OK;
 }
@@ -316,18 +393,22 @@ extern "C" int tsb_bn_bwd_reduce(const void* dy, int dycs, const void* y, int yc
 extern "C" int tsb_bn_bwd_apply(const void* dy, int dycs, const void* y, int ycs, const void* x, int xcs,
                                 const float* mean, const float* invstd, const float* gamma, const float* sum_dz,
                                 const float* sum_dz_xhat, double count, int relu, void* dx, int dxcs, void* dres,
-                                int drcs, long long npix, int C, tsb_stream_t stream) {
-    TSB_REQUIRE(dy && x && mean && invstd && gamma && sum_dz && sum_dz_xhat && dx && npix > 0 && count > 0 && (!relu || y),
-                "tsb_bn_bwd_apply: bad args");
+                                int drcs, long long npix, int C, float* dgamma_acc, float* dbeta_acc,
+                                const float* scale, const float* shift, tsb_stream_t stream) {
+    TSB_REQUIRE(dy && x && mean && invstd && gamma && sum_dz && sum_dz_xhat && dx && npix > 0 && count > 0, "tsb_bn_bwd_apply: bad args");
+    TSB_REQUIRE((dgamma_acc == nullptr) == (dbeta_acc == nullptr), "tsb_bn_bwd_apply: dgamma_acc and dbeta_acc go together");
+    const int mode = !relu ? 0 : (y ? 1 : 2);
+    TSB_REQUIRE(mode != 2 || (scale && shift), "tsb_bn_bwd_apply: relu without y needs scale and shift");
     TSB_REQUIRE(TSB_VEC_OK(C, dycs, dy) && TSB_VEC_OK(C, xcs, x) && TSB_VEC_OK(C, dxcs, dx) &&
-                (!relu || TSB_VEC_OK(C, ycs, y)) && (!dres || TSB_VEC_OK(C, drcs, dres)), "tsb_bn_bwd_apply: alignment");
+                (mode != 1 || TSB_VEC_OK(C, ycs, y)) && (!dres || TSB_VEC_OK(C, drcs, dres)), "tsb_bn_bwd_apply: alignment");
     int C8 = C / 8;
     int grid = tsb_grid_for(npix * C8, kThreads, 8);
     cudaStream_t st = (cudaStream_t)stream;
     float inv_count = (float)(1.0 / count);
-#define L(R, D) bn_bwd_apply_kernel<R, D><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, gamma, sum_dz, sum_dz_xhat, inv_count, (__nv_bfloat16*)dx, dxcs, (__nv_bfloat16*)dres, drcs, npix, C8)
-    if (relu) { if (dres) L(true, true); else L(true, false); }
-    else { if (dres) L(false, true); else L(false, false); }
+#define L(R, D) bn_bwd_apply_kernel<R, D><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (const __nv_bfloat16*)x, xcs, mean, invstd, gamma, sum_dz, sum_dz_xhat, inv_count, (__nv_bfloat16*)dx, dxcs, (__nv_bfloat16*)dres, drcs, npix, C8, dgamma_acc, dbeta_acc, scale, shift)
+    if (mode == 0) { if (dres) L(0, true); else L(0, false); }
+    else if (mode == 1) { if (dres) L(1, true); else L(1, false); }
+    else { if (dres) L(2, true); else L(2, false); }
 #undef L
     TSB_CUDA_CHECK_LAUNCH("bn_bwd_apply");
     return TSB_OK;

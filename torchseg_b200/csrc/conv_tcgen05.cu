@@ -587,7 +587,7 @@ int wgrad_common(WgParams& prm, int N, int P, int Q, int K, cudaStream_t st) {
     const int co_tiles = (K + 127) / 128;
     // split the pixel range so the grid covers ~2 waves of SMs, at least 8 tiles per CTA
     int base = groups * co_tiles;
-    int want = (2 * tsb_num_sms() + base - 1) / base;
+    int want = (convv2::g_wgrad_waves_x * tsb_num_sms() + base - 1) / base;
     int max_splits = (prm.total_tiles + 7) / 8;
     if (want > max_splits) want = max_splits;
     if (want < 1) want = 1;

@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_rows_kernel(const __grid_constan
 int g_use_base_offset = 0;  // measured on B200: the swizzle XOR is taken from the absolute smem address bits, so row-shifted starts need NO base_offset
 int g_allow_rows = 1;
 int g_allow_resident = 1;
+int g_wgrad_waves = 2;
 
 template <int BN, bool RES>
 int launch_v2(const V2Params& prm, int grid_x, int n_tiles, size_t smem, cudaStream_t st) {
@@ -492,6 +493,7 @@ extern "C" int tsb_debug_set(int key, int value) {
     else if (key == 2) g_allow_rows = value;
     else if (key == 3) g_allow_resident = value;
     else if (key == 4) convv2::g_enabled = value;
+    else if (key == 5) { g_wgrad_waves = value; convv2::g_wgrad_waves_x = value; }
     else return TSB_ERR_ARG;
     return TSB_OK;
 }
@@ -499,6 +501,7 @@ extern "C" int tsb_debug_set(int key, int value) {
 namespace convv2 {
 
 int g_enabled = 1;
+int g_wgrad_waves_x = 2;
 
 int launch(const Desc& d, cudaStream_t st) {
     V2Params prm;
@@ -670,7 +673,7 @@ int launch_wgrad_rows(const WgradDesc& d, cudaStream_t st) {
     const int co_tiles = (d.K + 127) / 128;
     const int zdim = ng * prm.cchunks;
     int base = zdim * co_tiles;
-    int want = (2 * tsb_num_sms() + base - 1) / base;
+    int want = (g_wgrad_waves * tsb_num_sms() + base - 1) / base;
     int max_splits = (prm.total_tiles + 15) / 16;
     if (want > max_splits) want = max_splits;
     if (want < 1) want = 1;

@@ -42,6 +42,7 @@ struct WgradDesc {
 };
 
 extern int g_enabled;
+extern int g_wgrad_waves_x;
 int launch(const Desc& d, cudaStream_t st);
 int launch_wgrad_rows(const WgradDesc& d, cudaStream_t st);
 

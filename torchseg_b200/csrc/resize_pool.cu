@@ -86,6 +86,7 @@ bilinear_bwd_kernel(const TO* __restrict__ dout, int ocs, TI* __restrict__ din, 
                     int Ho, int Wo, int accumulate) {
     const float ry = area_scale(Hi, Ho), rx = area_scale(Wi, Wo);
     const long long total = (long long)N * Hi * Wi * C8;
+    constexpr int kMaxCand = 12;  // candidate output columns kept in registers (up-scale factors >= 1/4 per side)
     for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
         int c8 = (int)(idx % C8);
         long long pix = idx / C8;
@@ -101,19 +102,42 @@ bilinear_bwd_kernel(const TO* __restrict__ dout, int ocs, TI* __restrict__ din, 
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
         const TO* base = dout + (long long)n * Ho * Wo * ocs + c8 * 8;
+        const bool small = (x_hi - x_lo + 1) <= kMaxCand;
+        float wxs[kMaxCand];
+        if (small) {
+#pragma unroll
+            for (int k = 0; k < kMaxCand; ++k) {
+                int x = x_lo + k;
+                Lerp lx = make_lerp(rx, min(x, Wo - 1), Wi);
+                wxs[k] = (x <= x_hi) ? ((lx.i0 == j ? lx.l0 : 0.f) + (lx.i1 == j ? lx.l1 : 0.f)) : 0.f;
+            }
+        }
         for (int y = y_lo; y <= y_hi; ++y) {
             Lerp ly = make_lerp(ry, y, Hi);
             float wy = (ly.i0 == i ? ly.l0 : 0.f) + (ly.i1 == i ? ly.l1 : 0.f);
             if (wy == 0.f) continue;
-            for (int x = x_lo; x <= x_hi; ++x) {
-                Lerp lx = make_lerp(rx, x, Wi);
-                float wx = (lx.i0 == j ? lx.l0 : 0.f) + (lx.i1 == j ? lx.l1 : 0.f);
-                if (wx == 0.f) continue;
-                float g[8];
-                Vec8<TO>::load(base + ((long long)y * Wo + x) * ocs, g);
-                float wgt = wy * wx;
+            if (small) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += wgt * g[k];
+                for (int k = 0; k < kMaxCand; ++k) {
+                    if (wxs[k] != 0.f) {
+                        float g[8];
+                        Vec8<TO>::load(base + ((long long)y * Wo + x_lo + k) * ocs, g);
+                        float wgt = wy * wxs[k];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] += wgt * g[e];
+                    }
+                }
+            } else {
+                for (int x = x_lo; x <= x_hi; ++x) {
+                    Lerp lx = make_lerp(rx, x, Wi);
+                    float wx = (lx.i0 == j ? lx.l0 : 0.f) + (lx.i1 == j ? lx.l1 : 0.f);
+                    if (wx == 0.f) continue;
+                    float g[8];
+                    Vec8<TO>::load(base + ((long long)y * Wo + x) * ocs, g);
+                    float wgt = wy * wx;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] += wgt * g[e];
+                }
             }
         }
         TI* dst = din + pix * ics + c8 * 8;
@@ -259,6 +283,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ics, __nv_bfloat16*
 }
 
 // backward, gather form: input pixel (h,w) belongs to <= 4 windows; it receives dout[p,q] iff idx[p,q] names it.
+// All (up to 4) index / gradient loads are issued before any is consumed (memory-level parallelism).
 __global__ void __launch_bounds__(kThreads)
 maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dout, int ocs,
                    __nv_bfloat16* __restrict__ din, int dcs, int N, int C8, int H, int W, int P, int Q) {
@@ -269,23 +294,32 @@ maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restr
         int w = (int)(pix % W);
         long long t = pix / W;
         int h = (int)(t % H), n = (int)(t / H);
+        const int p0 = h >> 1, p1 = (h + 1) >> 1, q0 = w >> 1, q1 = (w + 1) >> 1;  // windows with 2p-1 <= h <= 2p+1
+        uint2 pk[4];
+        uint4 gv[4];
+        uint32_t code[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int p = (k & 2) ? p1 : p0, q = (k & 1) ? q1 : q0;
+            ok[k] = (p < P) && (q < Q) && !((k & 2) && p1 == p0) && !((k & 1) && q1 == q0);
+            code[k] = (uint32_t)((h - (2 * p - 1)) * 3 + (w - (2 * q - 1)));
+            const long long opix = ((long long)n * P + (ok[k] ? p : 0)) * Q + (ok[k] ? q : 0);
+            pk[k] = __ldg(reinterpret_cast<const uint2*>(idx + opix * (long long)(C8 * 8) + c8 * 8));
+            gv[k] = __ldg(reinterpret_cast<const uint4*>(dout + opix * ocs + c8 * 8));
+        }
         float acc[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        for (int p = h / 2; p <= (h + 1) / 2; ++p) {  // windows with 2p-1 <= h <= 2p+1
-            if (p >= P) continue;
-            for (int q = w / 2; q <= (w + 1) / 2; ++q) {
-                if (q >= Q) continue;
-                const uint32_t code = (uint32_t)((h - (2 * p - 1)) * 3 + (w - (2 * q - 1)));
-                const long long opix = ((long long)n * P + p) * Q + q;
-                uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + opix * (long long)(C8 * 8) + c8 * 8));
-                float g[8];
-                Vec8<__nv_bfloat16>::load(dout + opix * ocs + c8 * 8, g);
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    uint32_t a = ((k < 4 ? pk.x : pk.y) >> ((k & 3) * 8)) & 0xffu;
-                    acc[k] += (a == code) ? g[k] : 0.f;
-                }
+        for (int k = 0; k < 4; ++k) {
+            if (!ok[k]) continue;
+            float g[8];
+            unpack8(gv[k], g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                uint32_t a = ((e < 4 ? pk[k].x : pk[k].y) >> ((e & 3) * 8)) & 0xffu;
+                acc[e] += (a == code[k]) ? g[e] : 0.f;
             }
         }
         Vec8<__nv_bfloat16>::store(din + pix * dcs + c8 * 8, acc);

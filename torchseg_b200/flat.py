@@ -21,6 +21,7 @@ def flatten(params, attr, like_data=True):
             if p.grad is not None:
                 view.copy_(p.grad)
             p.grad = view
+            p._tsb_direct = True   # kernels may accumulate straight into this persistent view (ops._direct_grad)
         spans.append((off, off + k))
         off += k
     return flat, spans
@@ -38,6 +39,7 @@ def ensure_flat_grads(params):
                 if p.grad is not None:
                     view.copy_(p.grad)
                 p.grad = view
+                p._tsb_direct = True
         return flat, spans
     flat, spans = flatten(params, "grad")
     ensure_flat_grads._reg = (key, flat, spans)

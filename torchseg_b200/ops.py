@@ -89,6 +89,7 @@ class _PackCache:
     def invalidate(self):
         self.step += 1
         self.cache.clear()
+        zero_arena.reset()
 
     def get(self, w, want_t, pad_k=None, stem=False):
         key = (id(w), w.data_ptr(), bool(want_t), pad_k, stem, w._version)
@@ -115,6 +116,53 @@ class _PackCache:
 
 
 pack_cache = _PackCache()
+
+
+class _ZeroArena(object):
+    """Small fp32 scratch buffers that must start at zero (BN statistics, reduction accumulators): carved out of ONE
+    buffer that is cleared with a single memset per step (`reset`, called from zero_grad / optimizer.step) instead of
+    one fill kernel per buffer. Falls back to torch.zeros when exhausted or never reset."""
+
+    def __init__(self, nfloats=1 << 20):
+        self.n = nfloats
+        self.buf = None
+        self.off = 0
+
+    def reset(self):
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off = 0
+
+    def take(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n4 = (n + 3) // 4 * 4
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.zeros(self.n, dtype=torch.float32, device=device)
+            self.off = 0
+        if self.off + n4 > self.n:
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        out = self.buf[self.off:self.off + n].view(shape)
+        self.off += n4
+        return out
+
+
+zero_arena = _ZeroArena()
+
+# set by the DDP shim: called with a parameter whose gradient has just been written DIRECTLY into its flat .grad view
+grad_ready_hook = None
+
+
+def _direct_grad(p):
+    """True when this parameter's .grad is a persistent flat-buffer view the kernels may accumulate into directly"""
+    return getattr(p, "_tsb_direct", False) and p.grad is not None
+
+
+def _notify(*params):
+    if grad_ready_hook is not None:
+        for p in params:
+            grad_ready_hook(p)
 
 # process group for SyncBN statistics (set by apex_shim.parallel.SyncBatchNorm / DistributedDataParallel)
 _sync = {"group": None, "world": 1}
@@ -246,10 +294,7 @@ class ConvBNActFn(torch.autograd.Function):
             N, C, H, W = x.shape
             P, Q = conv_out_size(H, R, stride, pad, dil), conv_out_size(W, R, stride, pad, dil)
         count = float(N * P * Q) * _sync["world"]
-        if training:
-            stats = torch.zeros((2, K), dtype=torch.float32, device=dev)
-        else:
-            stats = None
+        stats = zero_arena.take((2, K), dev) if training else None
         raw = nhwc_empty(N, K, P, Q, device=dev)
         if stem:
             wp, _ = pack_cache.get(w, False, stem=True)
@@ -274,6 +319,7 @@ class ConvBNActFn(torch.autograd.Function):
         call("tsb_bn_apply", ptr(raw), K, ptr(aux[2]), ptr(aux[3]), ptr(residual), cs_of(residual) if residual is not None else 0,
              int(relu), ptr(y), K, N * P * Q, K, stream())
         ctx.save_for_backward(x, w, gamma, raw, y, aux)
+        ctx.beta_ref = beta
         ctx.cfg = (stride, pad, dil, relu, stem, residual is not None, count, training)
         return y
 
@@ -289,23 +335,38 @@ class ConvBNActFn(torch.autograd.Function):
         npix = N * P * Q
         if dy.dtype != _BF or dy.stride(1) != 1:
             dy = to_nhwc(dy)
-        red = torch.zeros((2, K), dtype=torch.float32, device=dev)
-        call("tsb_bn_bwd_reduce", ptr(dy), cs_of(dy), ptr(y), K, ptr(raw), K, ptr(aux[0]), ptr(aux[1]), int(relu), npix, K,
-             ptr(red[0]), ptr(red[1]), stream())
+        red = zero_arena.take((2, K), dev)
+        # ReLU mask: recomputed from raw*scale+shift when there is no residual (saves reading y in both passes)
+        y_mask = ptr(y) if (relu and has_res) else None
+        call("tsb_bn_bwd_reduce", ptr(dy), cs_of(dy), y_mask, K, ptr(raw), K, ptr(aux[0]), ptr(aux[1]), int(relu), npix, K,
+             ptr(red[0]), ptr(red[1]), ptr(aux[2]), ptr(aux[3]), stream())
         # dgamma = Σ dz·x̂, dbeta = Σ dz are LOCAL sums (the DDP all-reduce averages parameter grads);
         # the dx formula needs the GLOBAL sums under SyncBN.
-        dgamma = red[1].clone()
-        dbeta = red[0].clone()
+        beta = ctx.beta_ref
+        direct = _direct_grad(w) and _direct_grad(gamma) and _direct_grad(beta)
+        fold = direct and _sync["world"] == 1   # single GPU: the accumulation is folded into tsb_bn_bwd_apply
+        if direct:
+            if not fold:
+                gamma.grad.add_(red[1])   # local sums must be taken before the SyncBN all-reduce
+                beta.grad.add_(red[0])
+            dgamma = dbeta = None
+        else:
+            dgamma = red[1].clone()
+            dbeta = red[0].clone()
         _allreduce_stats(red)
         draw = nhwc_empty(N, K, P, Q, device=dev)
         dres = nhwc_empty(N, K, P, Q, device=dev) if has_res else None
-        call("tsb_bn_bwd_apply", ptr(dy), cs_of(dy), ptr(y), K, ptr(raw), K, ptr(aux[0]), ptr(aux[1]), ptr(gamma), ptr(red[0]),
-             ptr(red[1]), count, int(relu), ptr(draw), K, ptr(dres), K if has_res else 0, npix, K, stream())
-        dw_view, dw = _new_wgrad(w)
+        call("tsb_bn_bwd_apply", ptr(dy), cs_of(dy), y_mask, K, ptr(raw), K, ptr(aux[0]), ptr(aux[1]), ptr(gamma), ptr(red[0]),
+             ptr(red[1]), count, int(relu), ptr(draw), K, ptr(dres), K if has_res else 0, npix, K,
+             ptr(gamma.grad) if fold else None, ptr(beta.grad) if fold else None, ptr(aux[2]), ptr(aux[3]), stream())
+        if direct:
+            dw_view, dw = None, w.grad.permute(0, 2, 3, 1)   # KRSC view of the flat gradient buffer
+        else:
+            dw_view, dw = _new_wgrad(w)
         dx = None
         if stem:
             H, W = P * 2, Q * 2
-            dwp = torch.zeros((K, 4, 64), dtype=torch.float32, device=dev)
+            dwp = zero_arena.take((K, 4, 64), dev)
             ev = conv_prof.begin()
             call("tsb_conv_stem_wgrad", ptr(x), N, H, W, ptr(draw), K, K, ptr(dwp), stream())
             conv_prof.end(ev, 2.0 * N * P * Q * K * 147)
@@ -315,6 +376,8 @@ class ConvBNActFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 _, wt = pack_cache.get(w, True)
                 dx = conv_dgrad(draw, wt, x.shape, K, R, stride, pad, dil)
+        if direct:
+            _notify(w, gamma, beta)
         return dx, dw_view, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
 
 
@@ -328,6 +391,7 @@ class ConvFn(torch.autograd.Function):
         wb, _ = pack_cache.get(w, False)
         y = conv_fprop(x, wb, K, R, stride, pad, dil, bias=bias, out_dtype=torch.float32 if out_f32 else _BF, ocs=ocs)
         ctx.save_for_backward(x, w)
+        ctx.bias_ref = bias
         ctx.cfg = (stride, pad, dil, bias is not None)
         return y
 
@@ -348,16 +412,24 @@ class ConvFn(torch.autograd.Function):
                 call("tsb_cast_scale", ptr(dy), _lib.dt(dy), cs_of(dy), ptr(dyb), BF16, Kp, N * P * Q, K, None, stream())
             else:
                 dyb[:, :K].copy_(dy)
-        dw_view, dw = _new_wgrad(w)
+        direct = _direct_grad(w) and (not has_bias or _direct_grad(ctx.bias_ref))
+        if direct:
+            dw_view, dw = None, w.grad.permute(0, 2, 3, 1)
+        else:
+            dw_view, dw = _new_wgrad(w)
         conv_wgrad(x, dyb[:, :K], K, R, stride, pad, dil, dw)
         db = None
         if has_bias:
-            db = torch.zeros((K,), dtype=torch.float32, device=dev)
+            db = ctx.bias_ref.grad if direct else torch.zeros((K,), dtype=torch.float32, device=dev)
             call("tsb_bias_grad", ptr(dyb), Kp, N * P * Q, K, ptr(db), stream())
+            if direct:
+                db = None
         dx = None
         if ctx.needs_input_grad[0]:
             _, wt = pack_cache.get(w, True, pad_k=Kp)
             dx = conv_dgrad(dyb, wt, x.shape, Kp, R, stride, pad, dil)
+        if direct:
+            _notify(*([w, ctx.bias_ref] if has_bias else [w]))
         return dx, dw_view, db, None, None, None, None, None
 
 

@@ -39,6 +39,7 @@ class SGD(object):
     def zero_grad(self, set_to_none=False):
         ensure_flat_grads(self._params)
         self.flat_grad.zero_()
+        ops.zero_arena.reset()
 
     def step(self, closure=None):
         ensure_flat_grads(self._params)
