@@ -291,6 +291,10 @@ def main():
         value = n_img / (ms / 1000.0)
         e2e_v = n_img / (ms_e2e / 1000.0)
         conv_tf = prof["flops"] / max(prof["ms"], 1e-9) / 1e9  # TFLOP/s over all conv launches of the region
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        if os.path.exists(tpath):  # DRAM bytes of the same launches from the committed ncu pass (per step)
+            traffic = json.load(open(tpath)).get("conv_dram_bytes_per_step")
         line = {
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -308,7 +312,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": conv_tf / peaks["tflops"], "traffic": None,
+                         "frac": conv_tf / peaks["tflops"], "traffic": traffic,
+                         "traffic_note": "dram__bytes_read+write summed over the conv launches of ONE step (profiles/r01_conv_traffic.json); algorithmic minimum ~5.9 GB/step",
+                         "flops_per_step": prof["flops"] / args.steps,
                          "kernel": "tcgen05 implicit-GEMM conv kernels (igemm_v2_kernel fprop/dgrad/stem + wgrad_rows_kernel/wgrad_mnmajor_kernel), all launches of the step",
                          "launches": prof["launches"], "kernel_ms_per_step": prof["ms"] / args.steps,
                          "peak_source": peaks["src"]},

@@ -1,0 +1,20 @@
+"""a handful of launches of the hot kernels at BASELINE size for `ncu --set full` (keep it short: ncu replays ~40x)"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torchseg_b200 import ops
+dev = torch.device("cuda:0")
+N, C, H, W, K = 16, 64, 256, 256, 64
+x = ops.nhwc_empty(N, C, H, W); x.normal_()
+wb = torch.randn(K, 3, 3, C, device=dev).to(torch.bfloat16)
+y = ops.nhwc_empty(N, K, H, W); gy = ops.nhwc_empty(N, K, H, W); gy.normal_()
+stats = torch.zeros(2, K, device=dev); dw = torch.zeros(K, 3, 3, C, device=dev)
+x2 = ops.nhwc_empty(N, 128, 128, 128); x2.normal_()
+wb2 = torch.randn(128, 3, 3, 128, device=dev).to(torch.bfloat16)
+y2 = ops.nhwc_empty(N, 128, 128, 128); st2 = torch.zeros(2, 128, device=dev)
+for _ in range(4):
+    ops.conv_fprop(x, wb, K, 3, 1, 1, 1, out=y, stats=stats)         # layer1 64->64 @256 (BN=64, resident weights, row tiles)
+    ops.conv_fprop(x2, wb2, 128, 3, 1, 1, 1, out=y2, stats=st2)      # layer2 128->128 @128 (BN=128, streamed weights)
+    ops.conv_wgrad(x, gy, K, 3, 1, 1, 1, dw)                          # layer1 wgrad (row tiles)
+torch.cuda.synchronize()
+print("ok")
