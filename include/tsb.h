@@ -69,8 +69,8 @@ int tsb_ohem_begin(uint32_t* state, tsb_stream_t stream);
 /* p_target from MATERIALISED logits (the reference boundary). logits: dtype F32/BF16, element
  * (n,c,y,x) at n*sn + c*sc + y*sy + x*sx (element strides; NCHW contiguous: sc=H*W, sy=W, sx=1).
  * labels int64 [N,H,W] contiguous. Writes p[N*H*W] (ignored pixels := 1.0f, loss_opr.py:81) and
- * nll[N*H*W] = -log_softmax(logits)[label] (0 for ignored); accumulates the level-0 radix histogram,
- * num_valid and count(p<=thresh) into state. */
+ * nll[N*H*W] = -log_softmax(logits)[label] (0 for ignored); accumulates num_valid and count(p<=thresh)
+ * into state (the radix histograms are built lazily by tsb_ohem_select, only when the k-th value is needed). */
 int tsb_ohem_ptarget(const void* logits, int dtype, long long sn, long long sc, long long sy, long long sx,
                      const int64_t* labels, int N, int C, int H, int W, int ignore_label, float thresh,
                      float* p, float* nll, uint32_t* state, tsb_stream_t stream);

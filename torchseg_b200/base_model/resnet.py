@@ -118,7 +118,10 @@ class ResNet(nn.Module):
     def forward(self, x):
         if self.deep_stem:
             raise NotImplementedError("deep-stem (v1c) C_in=3/32 convolutions are a later-round widening (SURVEY §8 C3-C5)")
-        x = conv_bn_act(x, self.conv1, self.bn1, True)
+        return self.forward_from_stem(conv_bn_act(x, self.conv1, self.bn1, True))
+
+    def forward_from_stem(self, x):
+        """stages after conv1 → bn1 → relu (the stem may be computed elsewhere, fused with a sibling stem)"""
         x = ops.MaxPool3x3S2Fn.apply(x)
         blocks = []
         x = self.layer1(x)

@@ -67,26 +67,21 @@ __device__ __forceinline__ void softmax_target(const float (&x)[CMAX], int C, in
     nll = logf(s) - (xt - m);
 }
 
-// shared tail of the two p_target kernels: writes p/nll, feeds histogram + counters
+// shared tail of the two p_target kernels: writes p/nll and counts num_valid / count(p <= thresh).
+// The radix histogram is NOT built here: it is only needed when count(p<=thresh) < k (tsb_ohem_select then
+// runs a level-0 histogram pass over p, 4 bytes/pixel), the common case skips it entirely.
 struct PtAccum {
     unsigned int num_valid = 0, count_le = 0;
 };
 __device__ __forceinline__ void pt_emit(long long i, bool valid, float p_t, float nll_v, float thresh, float* p,
-                                        float* nll, unsigned int* s_hist, PtAccum& acc) {
+                                        float* nll, PtAccum& acc) {
     float pv = valid ? p_t : 1.0f;  // loss_opr.py:81 masked_fill_(~valid, 1) then gather of class 0
     p[i] = pv;
     nll[i] = valid ? nll_v : 0.f;
     acc.num_valid += valid ? 1u : 0u;
     acc.count_le += (pv <= thresh) ? 1u : 0u;
-    unsigned int bin = __float_as_uint(pv) >> 20;
-    atomicAdd(&s_hist[bin > 4095u ? 4095u : bin], 1u);
 }
-__device__ __forceinline__ void pt_flush(unsigned int* s_hist, const PtAccum& acc, uint32_t* state, float* s_red) {
-    __syncthreads();
-    for (int b = threadIdx.x; b < 4096; b += kThreads) {
-        unsigned int v = s_hist[b];
-        if (v) atomicAdd(&state[ST_HIST + b], v);
-    }
+__device__ __forceinline__ void pt_flush(const PtAccum& acc, uint32_t* state, float* s_red) {
     float nv = block_sum<kThreads>((float)acc.num_valid, s_red);
     float cl = block_sum<kThreads>((float)acc.count_le, s_red);
     if (threadIdx.x == 0) {
@@ -101,10 +96,7 @@ __global__ void __launch_bounds__(kThreads)
 ohem_ptarget_kernel(const T* __restrict__ logits, long long sn, long long sc, long long sy, long long sx,
                     const int64_t* __restrict__ labels, int N, int C, int H, int W, int ignore_label, float thresh,
                     float* __restrict__ p, float* __restrict__ nll, uint32_t* state) {
-    __shared__ unsigned int s_hist[4096];
     __shared__ float s_red[33];
-    for (int b = threadIdx.x; b < 4096; b += kThreads) s_hist[b] = 0;
-    __syncthreads();
     PtAccum acc;
     const long long total = (long long)N * H * W;
     const long long hw = (long long)H * W;
@@ -122,9 +114,9 @@ ohem_ptarget_kernel(const T* __restrict__ logits, long long sn, long long sc, lo
             if (c < C) v[c] = ld_as_float<T>(base + c * sc);
         float p_t, nl;
         softmax_target<CMAX>(v, C, t, p_t, nl);
-        pt_emit(i, valid, p_t, nl, thresh, p, nll, s_hist, acc);
+        pt_emit(i, valid, p_t, nl, thresh, p, nll, acc);
     }
-    pt_flush(s_hist, acc, state, s_red);
+    pt_flush(acc, state, s_red);
 }
 
 // generic-C variant (C > 32, e.g. ADE 150 classes): two passes over the pixel's logits
@@ -133,10 +125,7 @@ __global__ void __launch_bounds__(kThreads)
 ohem_ptarget_kernel_anyc(const T* __restrict__ logits, long long sn, long long sc, long long sy, long long sx,
                          const int64_t* __restrict__ labels, int N, int C, int H, int W, int ignore_label,
                          float thresh, float* __restrict__ p, float* __restrict__ nll, uint32_t* state) {
-    __shared__ unsigned int s_hist[4096];
     __shared__ float s_red[33];
-    for (int b = threadIdx.x; b < 4096; b += kThreads) s_hist[b] = 0;
-    __syncthreads();
     PtAccum acc;
     const long long total = (long long)N * H * W;
     const long long hw = (long long)H * W;
@@ -159,9 +148,9 @@ ohem_ptarget_kernel_anyc(const T* __restrict__ logits, long long sn, long long s
         }
         float p_t = __fdiv_rn(et, s);
         float nl = logf(s) - (xt - m);
-        pt_emit(i, valid, p_t, nl, thresh, p, nll, s_hist, acc);
+        pt_emit(i, valid, p_t, nl, thresh, p, nll, acc);
     }
-    pt_flush(s_hist, acc, state, s_red);
+    pt_flush(acc, state, s_red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -194,10 +183,8 @@ __global__ void __launch_bounds__(kThreads)
 ohem_ptarget_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64_t* __restrict__ labels, int N,
                        int C, int H, int W, int ignore_label, float thresh, float* __restrict__ p,
                        float* __restrict__ nll, uint32_t* state, int maxcols) {
-    __shared__ unsigned int s_hist[4096];
     __shared__ float s_red[33];
     extern __shared__ float s_lo_dyn[];  // [2][maxcols][CMAX]: the two low-res source rows of this band
-    for (int b = threadIdx.x; b < 4096; b += kThreads) s_hist[b] = 0;
     PtAccum acc;
     const float ry = area_scale(h, H), rx = area_scale(w, W);
     const int n = blockIdx.z, ci = blockIdx.y, x0 = blockIdx.x * kStrip, x1 = min(W, x0 + kStrip);
@@ -228,9 +215,9 @@ ohem_ptarget_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const
             if (c < C) v[c] = lerp4(ly, lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c], s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
         float p_t, nl;
         softmax_target<CMAX>(v, C, t, p_t, nl);
-        pt_emit(i, valid, p_t, nl, thresh, p, nll, s_hist, acc);
+        pt_emit(i, valid, p_t, nl, thresh, p, nll, acc);
     }
-    pt_flush(s_hist, acc, state, s_red);
+    pt_flush(acc, state, s_red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,7 +229,7 @@ __global__ void __launch_bounds__(1024) ohem_decide_kernel(uint32_t* state, long
     __shared__ int s_bin;
     __shared__ unsigned long long s_before;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (level == 0) {
+    if (level < 0) {  // initial decision from the counters alone
         if (tid == 0) {
             unsigned int num_valid = state[ST_NUM_VALID];
             unsigned int count_le = state[ST_COUNT_LE];
@@ -258,7 +245,7 @@ __global__ void __launch_bounds__(1024) ohem_decide_kernel(uint32_t* state, long
             state[ST_PREFIX] = 0;
             state[ST_KREM] = (unsigned int)k;
         }
-        __syncthreads();
+        return;
     }
     const bool done = state[ST_DONE] != 0;
     if (!done) {
@@ -301,7 +288,7 @@ __global__ void __launch_bounds__(1024) ohem_decide_kernel(uint32_t* state, long
             int b = s_bin;
             unsigned int newk = krem - (unsigned int)s_before;
             if (level < 2) {
-                state[ST_PREFIX] = (prefix << 12) | (unsigned int)b;
+                state[ST_PREFIX] = (level == 0) ? (unsigned int)b : ((prefix << 12) | (unsigned int)b);
                 state[ST_KREM] = newk;
             } else {
                 unsigned int bits = (prefix << 8) | (unsigned int)b;
@@ -324,7 +311,10 @@ __global__ void __launch_bounds__(kThreads) ohem_hist_kernel(const float* __rest
     const unsigned int prefix = state[ST_PREFIX];
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
         unsigned int u = __float_as_uint(p[i]);
-        if (level == 1) {
+        if (level == 0) {
+            unsigned int bin = u >> 20;
+            atomicAdd(&s_hist[bin > 4095u ? 4095u : bin], 1u);
+        } else if (level == 1) {
             if ((u >> 20) == prefix) atomicAdd(&s_hist[(u >> 8) & 0xfffu], 1u);
         } else {
             if ((u >> 8) == prefix) atomicAdd(&s_hist[u & 0xffu], 1u);
@@ -614,16 +604,14 @@ extern "C" int tsb_ohem_select(const float* p, long long n, long long min_kept, 
     TSB_REQUIRE(p && state && n > 0, "tsb_ohem_select: bad args");
     cudaStream_t st = (cudaStream_t)stream;
     int grid = tsb_grid_for(n, kThreads, 8);
-    ohem_decide_kernel<<<1, 1024, 0, st>>>(state, n, min_kept, thresh, 0);
-    TSB_CUDA_CHECK_LAUNCH("ohem_decide0");
-    ohem_hist_kernel<<<grid, kThreads, 0, st>>>(p, n, state, 1);
-    TSB_CUDA_CHECK_LAUNCH("ohem_hist1");
-    ohem_decide_kernel<<<1, 1024, 0, st>>>(state, n, min_kept, thresh, 1);
-    TSB_CUDA_CHECK_LAUNCH("ohem_decide1");
-    ohem_hist_kernel<<<grid, kThreads, 0, st>>>(p, n, state, 2);
-    TSB_CUDA_CHECK_LAUNCH("ohem_hist2");
-    ohem_decide_kernel<<<1, 1024, 0, st>>>(state, n, min_kept, thresh, 2);
-    TSB_CUDA_CHECK_LAUNCH("ohem_decide2");
+    ohem_decide_kernel<<<1, 1024, 0, st>>>(state, n, min_kept, thresh, -1);
+    TSB_CUDA_CHECK_LAUNCH("ohem_decide_init");
+    for (int level = 0; level < 3; ++level) {  // every kernel early-exits on the device-side done flag
+        ohem_hist_kernel<<<grid, kThreads, 0, st>>>(p, n, state, level);
+        TSB_CUDA_CHECK_LAUNCH("ohem_hist");
+        ohem_decide_kernel<<<1, 1024, 0, st>>>(state, n, min_kept, thresh, level);
+        TSB_CUDA_CHECK_LAUNCH("ohem_decide");
+    }
     return TSB_OK;
 }
 

@@ -61,8 +61,21 @@ class BiSeNet(nn.Module):
 
     def features(self, data):
         """network.py:76-101 up to the three head inputs"""
-        spatial_out = self.spatial_path(data)
-        context_blocks = self.context_path(data)
+        sp, cp = self.spatial_path, self.context_path
+        if data.shape[1] == 3 and sp.conv_7x7.bn.training and cp.bn1.training:
+            # both 7x7/2 stems in ONE tensor-core launch over the shared space-to-depth image
+            from ..seg_opr.seg_oprs import _packed_image
+            bs, bc = sp.conv_7x7.bn, cp.bn1
+            s_stem, c_stem = ops.StemPairFn.apply(
+                _packed_image(data), sp.conv_7x7.conv.weight, bs.weight, bs.bias, bs.running_mean, bs.running_var,
+                cp.conv1.weight, bc.weight, bc.bias, bc.running_mean, bc.running_var,
+                float(bs.eps), float(bs.momentum if bs.momentum is not None else 0.1),
+                float(bc.eps), float(bc.momentum if bc.momentum is not None else 0.1))
+            spatial_out = sp.forward_from_stem(s_stem)
+            context_blocks = cp.forward_from_stem(c_stem)
+        else:
+            spatial_out = sp(data)
+            context_blocks = cp(data)
         context_blocks.reverse()
         gc = ops.AdaptiveAvgPoolFn.apply(context_blocks[0], 1)
         gc = self.global_context[1](gc)
@@ -110,7 +123,9 @@ class SpatialPath(nn.Module):
                                    has_relu=True, has_bias=False)
 
     def forward(self, x):
-        x = self.conv_7x7(x)
+        return self.forward_from_stem(self.conv_7x7(x))
+
+    def forward_from_stem(self, x):
         x = self.conv_3x3_1(x)
         x = self.conv_3x3_2(x)
         return self.conv_1x1(x)

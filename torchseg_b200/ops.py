@@ -381,6 +381,93 @@ class ConvBNActFn(torch.autograd.Function):
         return dx, dw_view, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
 
 
+class StemPairFn(torch.autograd.Function):
+    """The TWO 7x7/2 stems of BiSeNet (spatial_path.conv_7x7, bisenet network.py:118, and context_path.conv1,
+    resnet.py:126) read the same image: one tcgen05 launch computes both (K = 64 + 64 output channels, N = 128 MMA
+    tiles), one BN-apply pass normalises both, one wgrad launch produces both weight gradients. Returns the two
+    64-channel halves as channel-slice views of one NHWC buffer."""
+
+    @staticmethod
+    def forward(ctx, xs, w1, g1, b1, rm1, rv1, w2, g2, b2, rm2, rv2, eps1, mom1, eps2, mom2):
+        N, _, H2, WP = xs.shape
+        H, W, P, Q = H2 * 2, (WP - 4) * 2, H2, WP - 4
+        dev = xs.device
+        K1, K2 = w1.shape[0], w2.shape[0]
+        K = K1 + K2
+        wp = torch.empty((K, 4, 4, 16), dtype=_BF, device=dev)
+        call("tsb_pack_stem_weight", ptr(_krsc_ptr(w1)), K1, ptr(wp), stream())
+        call("tsb_pack_stem_weight", ptr(_krsc_ptr(w2)), K2, ptr(wp[K1:]), stream())
+        stats = zero_arena.take((2, K), dev)
+        raw = nhwc_empty(N, K, P, Q, device=dev)
+        # two N=64 launches into the channel halves of one buffer: this layer is bound by the epilogue's stores and the
+        # 64-column epilogue (one chunk per warp, register running sums) is the faster one; the wgrad below is fused
+        for off, Kh in ((0, K1), (K1, K2)):
+            ev = conv_prof.begin()
+            call("tsb_conv_stem_fprop", ptr(xs), N, H, W, ptr(wp[off:]), Kh, ptr(raw[:, off:]), K, ptr(stats[0][off:]),
+                 ptr(stats[1][off:]), stream())
+            conv_prof.end(ev, 2.0 * N * P * Q * Kh * 147)
+        _allreduce_stats(stats)
+        count = float(N * P * Q) * _sync["world"]
+        aux = torch.empty((4, K), dtype=torch.float32, device=dev)
+        for (off, Kh, g, b, rm, rv, eps, mom) in ((0, K1, g1, b1, rm1, rv1, eps1, mom1), (K1, K2, g2, b2, rm2, rv2, eps2, mom2)):
+            call("tsb_bn_finalize", ptr(stats[0][off:]), ptr(stats[1][off:]), count, Kh, ptr(g), ptr(b), eps, mom,
+                 ptr(aux[0][off:]), ptr(aux[1][off:]), ptr(aux[2][off:]), ptr(aux[3][off:]), ptr(rm), ptr(rv), stream())
+        y = nhwc_empty(N, K, P, Q, device=dev)
+        call("tsb_bn_apply", ptr(raw), K, ptr(aux[2]), ptr(aux[3]), None, 0, 1, ptr(y), K, N * P * Q, K, stream())
+        ctx.save_for_backward(xs, w1, g1, w2, g2, raw, aux)
+        ctx.refs = (b1, b2)
+        ctx.count = count
+        return y[:, :K1], y[:, K1:]
+
+    @staticmethod
+    def backward(ctx, dy1, dy2):
+        xs, w1, g1, w2, g2, raw, aux = ctx.saved_tensors
+        b1, b2 = ctx.refs
+        N, K, P, Q = raw.shape
+        K1 = w1.shape[0]
+        dev = raw.device
+        npix = N * P * Q
+        draw = nhwc_empty(N, K, P, Q, device=dev)
+        grads = []
+        for (off, w, g, b, dy) in ((0, w1, g1, b1, dy1), (K1, w2, g2, b2, dy2)):
+            Kh = w.shape[0]
+            if dy.dtype != _BF or dy.stride(1) != 1:
+                dy = to_nhwc(dy)
+            red = zero_arena.take((2, Kh), dev)
+            xr = raw[:, off:off + Kh]
+            call("tsb_bn_bwd_reduce", ptr(dy), cs_of(dy), None, 0, ptr(xr), K, ptr(aux[0][off:]), ptr(aux[1][off:]), 1, npix, Kh,
+                 ptr(red[0]), ptr(red[1]), ptr(aux[2][off:]), ptr(aux[3][off:]), stream())
+            direct = _direct_grad(w) and _direct_grad(g) and _direct_grad(b)
+            fold = direct and _sync["world"] == 1
+            if direct and not fold:
+                g.grad.add_(red[1])
+                b.grad.add_(red[0])
+            dg, db = (None, None) if direct else (red[1].clone(), red[0].clone())
+            _allreduce_stats(red)
+            call("tsb_bn_bwd_apply", ptr(dy), cs_of(dy), None, 0, ptr(xr), K, ptr(aux[0][off:]), ptr(aux[1][off:]), ptr(g),
+                 ptr(red[0]), ptr(red[1]), ctx.count, 1, ptr(draw[:, off:off + Kh]), K, None, 0, npix, Kh,
+                 ptr(g.grad) if fold else None, ptr(b.grad) if fold else None, ptr(aux[2][off:]), ptr(aux[3][off:]), stream())
+            grads.append((direct, dg, db))
+        H, W = P * 2, Q * 2
+        dwp = zero_arena.take((K, 4, 64), dev)
+        ev = conv_prof.begin()
+        call("tsb_conv_stem_wgrad", ptr(xs), N, H, W, ptr(draw), K, K, ptr(dwp), stream())
+        conv_prof.end(ev, 2.0 * N * P * Q * K * 147)
+        outs = []
+        for (off, w, g, b), (direct, dg, db) in zip(((0, w1, g1, b1), (K1, w2, g2, b2)), grads):
+            Kh = w.shape[0]
+            if direct:
+                dwv, dw = None, w.grad.permute(0, 2, 3, 1)
+            else:
+                dwv, dw = _new_wgrad(w)
+            call("tsb_unpack_stem_wgrad", ptr(dwp[off:]), Kh, ptr(dw), stream())
+            if direct:
+                _notify(w, g, b)
+            outs.append((dwv, dg, db))
+        (dw1, dg1, db1), (dw2, dg2, db2) = outs
+        return None, dw1, dg1, db1, None, None, dw2, dg2, db2, None, None, None, None, None, None
+
+
 class ConvFn(torch.autograd.Function):
     """plain convolution (+bias), bf16 or fp32 output with channel stride `ocs` — the 1x1 classifier heads
     (bisenet network.py:156-161) and the BN-free SE convs of FeatureFusion (seg_oprs.py:224-229)."""
