@@ -574,6 +574,19 @@ class AdaptiveAvgPoolFn(torch.autograd.Function):
         return dx, None
 
 
+_scalars = {}
+
+
+def _const_scalar(v, device):
+    """cached 1-element fp32 device tensor (scale factors read by kernels from device memory)"""
+    key = (v, str(device))
+    t = _scalars.get(key)
+    if t is None:
+        t = torch.tensor([v], dtype=torch.float32, device=device)
+        _scalars[key] = t
+    return t
+
+
 class BilinearFn(torch.autograd.Function):
     """F.interpolate(mode='bilinear', align_corners=True) — bisenet network.py:82-84,93-94"""
 
@@ -591,7 +604,14 @@ class BilinearFn(torch.autograd.Function):
         if dy.dtype != _BF or dy.stride(1) != 1:
             dy = to_nhwc(dy)
         dx = nhwc_empty(N, C, Hi, Wi, device=dy.device)
-        call("tsb_bilinear_bwd", ptr(dy), BF16, cs_of(dy), ptr(dx), BF16, C, N, C, Hi, Wi, Ho, Wo, 0, stream())
+        if Hi == 1 and Wi == 1:
+            # broadcast forward (1x1 → HxW, bisenet network.py:82-84) ⇒ the backward is a plain spatial sum: reuse the
+            # pooling reduction (mean) and scale by H*W instead of a one-block gather
+            m32 = torch.empty((N, 1, 1, C), dtype=torch.float32, device=dy.device)
+            call("tsb_adaptive_avgpool_fwd", ptr(dy), cs_of(dy), N, C, Ho, Wo, 1, ptr(m32), stream())
+            call("tsb_cast_scale", ptr(m32), F32, C, ptr(dx), BF16, C, N, C, ptr(_const_scalar(float(Ho * Wo), dy.device)), stream())
+        else:
+            call("tsb_bilinear_bwd", ptr(dy), BF16, cs_of(dy), ptr(dx), BF16, C, N, C, Hi, Wi, Ho, Wo, 0, stream())
         return dx, None, None
 
 
