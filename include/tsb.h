@@ -187,10 +187,11 @@ int tsb_pack_image_s2d(const float* img, int N, int H, int W, void* out, tsb_str
 /* fp32 [K,R,S,C] weights (KRSC == channels_last OIHW) → bf16 copy and bf16 flipped-transposed
  * [C,R,S,K] copy for dgrad (either output may be NULL) */
 int tsb_pack_weight(const float* w, int K, int R, int S, int C, void* w_bf16, void* wt_bf16, tsb_stream_t stream);
-/* 7x7x3 stem weights [K,7,7,3] fp32 → s2d-packed bf16 [K,4,4,16] ; and the reverse for gradients
- * (dW[K,7,7,3] += unpack(dWp[K,4,4,16] fp32)) */
-int tsb_pack_stem_weight(const float* w, int K, void* wp_bf16, tsb_stream_t stream);
-int tsb_unpack_stem_wgrad(const float* dwp, int K, float* dw, tsb_stream_t stream);
+/* RxRx3 stride-2 stem weights [K,R,R,3] fp32 (R = 7 pad 3: resnet.py:126 / bisenet network.py:118; R = 3 pad 1:
+ * the v1c deep stem resnet.py:111-112) → s2d-packed bf16 [K,4,4,16]; and the reverse for gradients
+ * (dW[K,R,R,3] += unpack(dWp[K,4,4,16] fp32)) */
+int tsb_pack_stem_weight(const float* w, int K, int R, void* wp_bf16, tsb_stream_t stream);
+int tsb_unpack_stem_wgrad(const float* dwp, int K, int R, float* dw, tsb_stream_t stream);
 /* elementwise: dst = (dtype)src * (*scale_dev or 1) ; strided NHWC channel slices, C multiple of 8 */
 int tsb_cast_scale(const void* src, int sdtype, int scs, void* dst, int ddtype, int dcs, long long npix, int C,
                    const float* scale_dev, tsb_stream_t stream);
@@ -226,7 +227,7 @@ int tsb_conv2d_dgrad(const tsb_conv_shape* s, const void* dy, int dycs, const vo
 /* wgrad: dw[K,R,S,C] (fp32, KRSC) += Σ_pixels dy ⊗ x  (red.global.add.f32; caller zeroes or accumulates) */
 int tsb_conv2d_wgrad(const tsb_conv_shape* s, const void* x, int xcs, const void* dy, int dycs, float* dw,
                      tsb_stream_t stream);
-/* 7x7 stride-2 pad-3 stem on the s2d-packed image (tsb_pack_image_s2d / tsb_pack_stem_weight):
+/* stride-2 C_in=3 stem (7x7 pad 3 or 3x3 pad 1, same packed weight format) on the s2d-packed image (tsb_pack_image_s2d / tsb_pack_stem_weight):
  * xs2d [N,H/2,W/2+4,16] bf16, wp [K,4,4,16] bf16 → y [N,H/2,W/2,K]. */
 int tsb_conv_stem_fprop(const void* xs2d, int N, int H, int W, const void* wp, int K, void* y, int ycs, float* sum,
                         float* sumsq, tsb_stream_t stream);

@@ -226,3 +226,76 @@ def fcn_r18_loss(data, label, sd, aux_ratio=0.5, ignore_label=255, eps=1e-5, mom
     aux = F.interpolate(aux, scale_factor=16, mode="bilinear", align_corners=True)
     loss = F.cross_entropy(pred, label, ignore_index=ignore_label)
     return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label)
+
+
+# --------------------------------------------------------------------------------------------------
+# PSPNet-R101_v1c dilated-8 — /root/reference/model/pspnet/ade.pspnet.R101_v1c/network.py:14-109
+# --------------------------------------------------------------------------------------------------
+def bottleneck(x, sd, prefix, stride, dil2, has_down, down_stride, eps, momentum, training, stats=None):
+    """Bottleneck.forward — /root/reference/furnace/base_model/resnet.py:78-101 (conv2 carries stride / dilation)"""
+    out = q(F.conv2d(x, qw(sd[prefix + ".conv1.weight"])))
+    out = q(F.relu(_bn(out, sd, prefix + ".bn1", eps, momentum, training, stats)))
+    out = q(F.conv2d(out, qw(sd[prefix + ".conv2.weight"]), None, stride, dil2, dil2))
+    out = q(F.relu(_bn(out, sd, prefix + ".bn2", eps, momentum, training, stats)))
+    out = q(F.conv2d(out, qw(sd[prefix + ".conv3.weight"])))
+    out = _bn(out, sd, prefix + ".bn3", eps, momentum, training, stats)
+    residual = x
+    if has_down:
+        residual = q(F.conv2d(x, qw(sd[prefix + ".downsample.0.weight"]), None, down_stride))
+        residual = q(_bn(residual, sd, prefix + ".downsample.1", eps, momentum, training, stats))
+    return q(F.relu(out + residual))
+
+
+def resnet_v1c_d8(x, sd, prefix, layers, eps, momentum, training, stats=None):
+    """ResNet.forward with deep stem (resnet.py:110-124,168-184) after PSPNet._nostride_dilate(layer3, 2) and
+    (layer4, 4) (pspnet network.py:22-23,62-72): stride-2 3x3 → stride 1, dilation=padding=d//2; other 3x3 → d;
+    the stride-2 1x1 downsample → stride 1."""
+    c = prefix + ".conv1"
+    x = q(F.conv2d(q(x), qw(sd[c + ".0.weight"]), None, 2, 1))
+    x = q(F.relu(_bn(x, sd, c + ".1", eps, momentum, training, stats)))
+    x = q(F.conv2d(x, qw(sd[c + ".3.weight"]), None, 1, 1))
+    x = q(F.relu(_bn(x, sd, c + ".4", eps, momentum, training, stats)))
+    x = q(F.conv2d(x, qw(sd[c + ".6.weight"]), None, 1, 1))
+    x = q(F.relu(_bn(x, sd, prefix + ".bn1", eps, momentum, training, stats)))
+    x = F.max_pool2d(x, 3, 2, 1)
+    blocks = []
+    for li, nblk in enumerate(layers, start=1):
+        for bi in range(nblk):
+            pre = "%s.layer%d.%d" % (prefix, li, bi)
+            first = bi == 0
+            if li == 1:
+                stride, dil2, dstride = 1, 1, 1
+            elif li == 2:
+                stride, dil2, dstride = (2 if first else 1), 1, 2
+            elif li == 3:      # dilate = 2
+                stride, dil2, dstride = 1, (1 if first else 2), 1
+            else:              # dilate = 4
+                stride, dil2, dstride = 1, (2 if first else 4), 1
+            x = bottleneck(x, sd, pre, stride, dil2, first, dstride, eps, momentum, training, stats)
+        blocks.append(x)
+    return blocks
+
+
+def pyramid_pooling_logits(x, sd, prefix, eps, momentum, training, scales=(1, 2, 3, 6), stats=None):
+    """PyramidPooling.forward — pspnet network.py:99-109 (Dropout2d disabled: p = 0 in the parity runs)"""
+    outs = [x]
+    for i, s in enumerate(scales):
+        p = q(F.adaptive_avg_pool2d(x, s))
+        p = conv_bn_relu(p, sd, "%s.ppm.%d.psp/cbr" % (prefix, i), 1, 0, eps=eps, momentum=momentum, training=training,
+                         stats=stats)
+        outs.append(q(F.interpolate(p, size=x.shape[2:], mode="bilinear", align_corners=True)))
+    fm = torch.cat(outs, 1)
+    fm = conv_bn_relu(fm, sd, prefix + ".conv6.0", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
+    return F.conv2d(fm, qw(sd[prefix + ".conv6.2.weight"]), sd[prefix + ".conv6.2.bias"])
+
+
+def pspnet_loss(data, label, sd, layers=(3, 4, 23, 3), aux_ratio=0.4, ignore_label=-1, eps=1e-5, momentum=0.1, stats=None):
+    """PSPNet.forward training branch — pspnet network.py:40-57 (x8 bilinear, log_softmax, CE; loss + 0.4*aux)"""
+    blocks = resnet_v1c_d8(data, sd, "backbone", layers, eps, momentum, True, stats)
+    psp = pyramid_pooling_logits(blocks[-1], sd, "psp_layer", eps, momentum, True, stats=stats)
+    aux = conv_bn_relu(blocks[-2], sd, "aux_layer.0", 1, 1, eps=eps, momentum=momentum, training=True, stats=stats)
+    aux = F.conv2d(aux, qw(sd["aux_layer.2.weight"]), sd["aux_layer.2.bias"])
+    psp = F.log_softmax(F.interpolate(psp, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+    aux = F.log_softmax(F.interpolate(aux, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+    loss = F.cross_entropy(psp, label, ignore_index=ignore_label)
+    return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label), (psp, aux)

@@ -40,3 +40,11 @@ def fcn_case(N=2, HW=256, seed=304):
     y = torch.randint(0, 19, (N, HW, HW), generator=g, dtype=torch.int64)
     y[:, : HW // 10, :] = 255
     return x, y, seed
+
+
+def pspnet_case(N=2, HW=96, seed=4, classes=150):
+    """BASELINE configs[2] shape family (PSPNet R101_v1c dilated-8, ADE 150 classes, ignore -1), small spatial size"""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, 3, HW, HW, generator=g)
+    y = torch.randint(-1, classes, (N, HW, HW), generator=g, dtype=torch.int64)
+    return x, y, seed

@@ -106,24 +106,24 @@ def test_conv_dgrad_accumulate(cuda):
     assert rel_err(out, ref) < 1e-2
 
 
-@pytest.mark.parametrize("HW", [(64, 64), (32, 96)])
-def test_stem_7x7(cuda, HW):
-    """7x7/2 stem through the space-to-depth pack (fprop + wgrad)"""
+@pytest.mark.parametrize("HW,R", [((64, 64), 7), ((32, 96), 7), ((48, 80), 3)])
+def test_stem_7x7(cuda, HW, R):
+    """7x7/2 (pad 3) and 3x3/2 (pad 1, v1c deep stem) C_in=3 stems through the space-to-depth pack (fprop + wgrad)"""
     from torchseg_b200 import ops
     H, W = HW
     g = torch.Generator().manual_seed(3)
     N, K = 2, 64
     img = torch.randn(N, 3, H, W, generator=g)
-    w = bf16_round(torch.randn(K, 3, 7, 7, generator=g) / 12)
+    w = bf16_round(torch.randn(K, 3, R, R, generator=g) / 12)
     img_b = bf16_round(img)
     gy = bf16_round(torch.randn(N, K, H // 2, W // 2, generator=g))
     wr = w.clone().requires_grad_(True)
-    y_ref = F.conv2d(img_b, wr, None, 2, 3)
+    y_ref = F.conv2d(img_b, wr, None, 2, (R - 1) // 2)
     y_ref.backward(gy)
     xs = ops.pack_image_s2d(img.to(cuda))
     wk = w.to(cuda).permute(0, 2, 3, 1).contiguous()
     wp = torch.empty((K, 4, 4, 16), dtype=torch.bfloat16, device=cuda)
-    ops.call("tsb_pack_stem_weight", ops.ptr(wk), K, ops.ptr(wp), ops.stream())
+    ops.call("tsb_pack_stem_weight", ops.ptr(wk), K, R, ops.ptr(wp), ops.stream())
     y = ops.nhwc_empty(N, K, H // 2, W // 2)
     stats = torch.zeros(2, K, device=cuda)
     ops.call("tsb_conv_stem_fprop", ops.ptr(xs), N, H, W, ops.ptr(wp), K, ops.ptr(y), K, ops.ptr(stats[0]), ops.ptr(stats[1]),
@@ -132,8 +132,8 @@ def test_stem_7x7(cuda, HW):
     assert rel_err(y, y_ref) < 1e-2
     dwp = torch.zeros((K, 4, 64), device=cuda)
     ops.call("tsb_conv_stem_wgrad", ops.ptr(xs), N, H, W, ops.ptr(ops.to_nhwc(gy.to(cuda))), K, K, ops.ptr(dwp), ops.stream())
-    dw = torch.zeros((K, 7, 7, 3), device=cuda)
-    ops.call("tsb_unpack_stem_wgrad", ops.ptr(dwp), K, ops.ptr(dw), ops.stream())
+    dw = torch.zeros((K, R, R, 3), device=cuda)
+    ops.call("tsb_unpack_stem_wgrad", ops.ptr(dwp), K, R, ops.ptr(dw), ops.stream())
     torch.cuda.synchronize()
     assert rel_err(dw.permute(0, 3, 1, 2), wr.grad) < 1e-2
 

@@ -16,7 +16,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
 from oracle import reference_live as rl  # noqa: E402
-from golden_cases import ohem_case, bisenet_case, fcn_case, OHEM_REGIMES  # noqa: E402
+from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, OHEM_REGIMES  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -84,6 +84,23 @@ def main():
     aux = F.interpolate(aux_head(blocks[-2]), scale_factor=16, mode='bilinear', align_corners=True)
     ce = nn.CrossEntropyLoss(ignore_index=255)
     gold["fcn_r18"] = {"loss": float(ce(pred, y) + 0.5 * ce(aux, y))}
+
+    # PSPNet-R101_v1c dilated-8 (BASELINE configs[2] family), Dropout2d disabled
+    psp = rl.load_network('pspnet/ade.pspnet.R101_v1c', num_classes=150)
+    x, y, seed = pspnet_case()
+    torch.manual_seed(seed)
+    m = psp.PSPNet(150, nn.CrossEntropyLoss(reduction='mean', ignore_index=-1), None, nn.BatchNorm2d)
+    for mod in m.modules():
+        if isinstance(mod, nn.Dropout2d):
+            mod.p = 0.0
+    m.train()
+    loss = m(x, y)
+    loss.backward()
+    gold["pspnet_r101"] = {"loss": float(loss), "n_params": sum(p.numel() for p in m.parameters()),
+                           "n_state": len(m.state_dict()),
+                           "grad_norms": {n: float(p.grad.norm()) for n, p in m.named_parameters()
+                                          if n in ("backbone.conv1.0.weight", "backbone.layer3.5.conv2.weight",
+                                                   "psp_layer.conv6.0.conv.weight", "aux_layer.2.weight")}}
 
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "reference_outputs.json"), "w") as f:

@@ -52,8 +52,8 @@ _SIGS = {
     "tsb_chan_scale_bwd": [P, I, P, I, P, F, P, I, P, I, I, I, P],
     "tsb_pack_image_s2d": [P, I, I, I, P, P],
     "tsb_pack_weight": [P, I, I, I, I, P, P, P],
-    "tsb_pack_stem_weight": [P, I, P, P],
-    "tsb_unpack_stem_wgrad": [P, I, P, P],
+    "tsb_pack_stem_weight": [P, I, I, P, P],
+    "tsb_unpack_stem_wgrad": [P, I, I, P, P],
     "tsb_cast_scale": [P, I, I, P, I, I, L, I, P, P],
     "tsb_add": [P, I, P, I, P, I, L, I, P],
     "tsb_conv2d_fprop": [P, P, I, P, P, P, I, I, P, P, P],

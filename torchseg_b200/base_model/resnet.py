@@ -117,7 +117,13 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         if self.deep_stem:
-            raise NotImplementedError("deep-stem (v1c) C_in=3/32 convolutions are a later-round widening (SURVEY §8 C3-C5)")
+            # v1c stem (resnet.py:110-124): 3x3/2 (C_in = 3, space-to-depth stem kernel) → 3x3 → 3x3, then bn1 + relu
+            c = self.conv1
+            if c[3].in_channels % 64 != 0:
+                raise NotImplementedError("deep stem needs stem_width % 64 == 0 (BASELINE configs use stem_width=64)")
+            x = conv_bn_act(x, c[0], c[1], True)
+            x = conv_bn_act(x, c[3], c[4], True)
+            return self.forward_from_stem(conv_bn_act(x, c[6], self.bn1, True))
         return self.forward_from_stem(conv_bn_act(x, self.conv1, self.bn1, True))
 
     def forward_from_stem(self, x):

@@ -54,32 +54,33 @@ pack_weight_kernel(const float* __restrict__ w, int K, int R, int S, int C, __nv
     }
 }
 
-// stem: w [K,7,7,3] (KRSC fp32) → wp [K,4(a),4(b),16] bf16 where original tap r = 2a+py-1... see below.
-// conv: out(oh,ow) = Σ_{r,s} W[r,s]·X[2oh+r-3, 2ow+s-3];  r-3 = 2*(a-2)+py, a∈[0,4), py∈{0,1} → r = 2a+py-1
-__device__ __forceinline__ bool stem_map(int a, int b, int e, int& r, int& s, int& c) {
+// stem: w [K,R,R,3] (KRSC fp32, stride-2 conv with pad = (R-1)/2, R = 7 or 3) → wp [K,4(a),4(b),16] bf16.
+// conv: out(oh,ow) = Σ_{r,s} W[r,s]·X[2oh+r-pad, 2ow+s-pad];  r-pad = 2*(a-2)+py, a∈[0,4), py∈{0,1}
+//   → r = 2a + py - (4 - pad)   (R=7,pad=3: r = 2a+py-1;  R=3,pad=1: r = 2a+py-3, only a ∈ {1,2} carry weights)
+__device__ __forceinline__ bool stem_map(int a, int b, int e, int R, int pad, int& r, int& s, int& c) {
     if (e >= 12) return false;
     int q = e / 3;
     c = e % 3;
     int py = q >> 1, px = q & 1;
-    r = 2 * a + py - 1;
-    s = 2 * b + px - 1;
-    return r >= 0 && r < 7 && s >= 0 && s < 7;
+    r = 2 * a + py - (4 - pad);
+    s = 2 * b + px - (4 - pad);
+    return r >= 0 && r < R && s >= 0 && s < R;
 }
-__global__ void pack_stem_weight_kernel(const float* __restrict__ w, int K, __nv_bfloat16* __restrict__ wp) {
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, int K, int R, int pad, __nv_bfloat16* __restrict__ wp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * 256) return;
     int e = i & 15, b = (i >> 4) & 3, a = (i >> 6) & 3, k = i >> 8;
     int r, s, c;
     float v = 0.f;
-    if (stem_map(a, b, e, r, s, c)) v = w[((k * 7 + r) * 7 + s) * 3 + c];
+    if (stem_map(a, b, e, R, pad, r, s, c)) v = w[((k * R + r) * R + s) * 3 + c];
     wp[i] = __float2bfloat16_rn(v);
 }
-__global__ void unpack_stem_wgrad_kernel(const float* __restrict__ dwp, int K, float* __restrict__ dw) {
+__global__ void unpack_stem_wgrad_kernel(const float* __restrict__ dwp, int K, int R, int pad, float* __restrict__ dw) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * 256) return;
     int e = i & 15, b = (i >> 4) & 3, a = (i >> 6) & 3, k = i >> 8;
     int r, s, c;
-    if (stem_map(a, b, e, r, s, c)) dw[((k * 7 + r) * 7 + s) * 3 + c] += dwp[i];  // (a,b,e) ↔ (r,s,c) is 1:1
+    if (stem_map(a, b, e, R, pad, r, s, c)) dw[((k * R + r) * R + s) * 3 + c] += dwp[i];  // (a,b,e) ↔ (r,s,c) is 1:1
 }
 
 template <typename TS, typename TD>
@@ -226,16 +227,18 @@ extern "C" int tsb_pack_weight(const float* w, int K, int R, int S, int C, void*
     return TSB_OK;
 }
 
-extern "C" int tsb_pack_stem_weight(const float* w, int K, void* wp_bf16, tsb_stream_t stream) {
+extern "C" int tsb_pack_stem_weight(const float* w, int K, int R, void* wp_bf16, tsb_stream_t stream) {
     TSB_REQUIRE(w && wp_bf16 && K > 0, "tsb_pack_stem_weight: bad args");
-    pack_stem_weight_kernel<<<(K * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, K, (__nv_bfloat16*)wp_bf16);
+    TSB_REQUIRE(R == 7 || R == 3, "tsb_pack_stem_weight: R must be 7 (pad 3) or 3 (pad 1)");
+    pack_stem_weight_kernel<<<(K * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, K, R, (R - 1) / 2, (__nv_bfloat16*)wp_bf16);
     TSB_CUDA_CHECK_LAUNCH("pack_stem_weight");
     return TSB_OK;
 }
 
-extern "C" int tsb_unpack_stem_wgrad(const float* dwp, int K, float* dw, tsb_stream_t stream) {
+extern "C" int tsb_unpack_stem_wgrad(const float* dwp, int K, int R, float* dw, tsb_stream_t stream) {
     TSB_REQUIRE(dwp && dw && K > 0, "tsb_unpack_stem_wgrad: bad args");
-    unpack_stem_wgrad_kernel<<<(K * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dwp, K, dw);
+    TSB_REQUIRE(R == 7 || R == 3, "tsb_unpack_stem_wgrad: R must be 7 (pad 3) or 3 (pad 1)");
+    unpack_stem_wgrad_kernel<<<(K * 256 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dwp, K, R, (R - 1) / 2, dw);
     TSB_CUDA_CHECK_LAUNCH("unpack_stem_wgrad");
     return TSB_OK;
 }

@@ -1,2 +1,3 @@
 from .bisenet import BiSeNet, SpatialPath, BiSeNetHead
 from .fcn import FCN
+from .pspnet import PSPNet, PyramidPooling

@@ -99,7 +99,7 @@ class _PackCache:
         K, C, R, S = w.shape
         if stem:
             wp = torch.empty((K, 4, 4, 16), dtype=_BF, device=w.device)
-            call("tsb_pack_stem_weight", ptr(_krsc_ptr(w)), K, ptr(wp), stream())
+            call("tsb_pack_stem_weight", ptr(_krsc_ptr(w)), K, R, ptr(wp), stream())
             out = (wp, None, weakref.ref(w))
         else:
             src = _krsc_ptr(w)
@@ -370,7 +370,7 @@ class ConvBNActFn(torch.autograd.Function):
             ev = conv_prof.begin()
             call("tsb_conv_stem_wgrad", ptr(x), N, H, W, ptr(draw), K, K, ptr(dwp), stream())
             conv_prof.end(ev, 2.0 * N * P * Q * K * 147)
-            call("tsb_unpack_stem_wgrad", ptr(dwp), K, ptr(dw), stream())
+            call("tsb_unpack_stem_wgrad", ptr(dwp), K, R, ptr(dw), stream())
         else:
             conv_wgrad(x, draw, K, R, stride, pad, dil, dw)
             if ctx.needs_input_grad[0]:
@@ -395,8 +395,8 @@ class StemPairFn(torch.autograd.Function):
         K1, K2 = w1.shape[0], w2.shape[0]
         K = K1 + K2
         wp = torch.empty((K, 4, 4, 16), dtype=_BF, device=dev)
-        call("tsb_pack_stem_weight", ptr(_krsc_ptr(w1)), K1, ptr(wp), stream())
-        call("tsb_pack_stem_weight", ptr(_krsc_ptr(w2)), K2, ptr(wp[K1:]), stream())
+        call("tsb_pack_stem_weight", ptr(_krsc_ptr(w1)), K1, w1.shape[2], ptr(wp), stream())
+        call("tsb_pack_stem_weight", ptr(_krsc_ptr(w2)), K2, w2.shape[2], ptr(wp[K1:]), stream())
         stats = zero_arena.take((2, K), dev)
         raw = nhwc_empty(N, K, P, Q, device=dev)
         # two N=64 launches into the channel halves of one buffer: this layer is bound by the epilogue's stores and the
@@ -460,7 +460,7 @@ class StemPairFn(torch.autograd.Function):
                 dwv, dw = None, w.grad.permute(0, 2, 3, 1)
             else:
                 dwv, dw = _new_wgrad(w)
-            call("tsb_unpack_stem_wgrad", ptr(dwp[off:]), Kh, ptr(dw), stream())
+            call("tsb_unpack_stem_wgrad", ptr(dwp[off:]), Kh, w.shape[2], ptr(dw), stream())
             if direct:
                 _notify(w, g, b)
             outs.append((dwv, dg, db))
@@ -648,25 +648,32 @@ class ChanScaleFn(torch.autograd.Function):
 
 
 class ConcatFn(torch.autograd.Function):
-    """torch.cat([x1, x2], dim=1) (FeatureFusion, seg_oprs.py:234) as two strided copies into one NHWC buffer;
-    backward hands out channel-slice views (no copy)."""
+    """torch.cat([x1, x2, ...], dim=1) (FeatureFusion seg_oprs.py:234, PyramidPooling pspnet network.py:106) as strided
+    copies into ONE NHWC buffer; backward hands out channel-slice views (no copy)."""
 
     @staticmethod
-    def forward(ctx, x1, x2):
-        N, C1, H, W = x1.shape
-        C2 = x2.shape[1]
-        out = nhwc_empty(N, C1 + C2, H, W, device=x1.device)
+    def forward(ctx, *xs):
+        N, _, H, W = xs[0].shape
+        chans = [int(x.shape[1]) for x in xs]
+        Ct = sum(chans)
+        out = nhwc_empty(N, Ct, H, W, device=xs[0].device)
         npix = N * H * W
-        call("tsb_cast_scale", ptr(x1), BF16, cs_of(x1), ptr(out), BF16, C1 + C2, npix, C1, None, stream())
-        call("tsb_cast_scale", ptr(x2), BF16, cs_of(x2), ptr(out[:, C1:]), BF16, C1 + C2, npix, C2, None, stream())
-        ctx.c1 = C1
+        off = 0
+        for x, c in zip(xs, chans):
+            call("tsb_cast_scale", ptr(x), BF16, cs_of(x), ptr(out[:, off:]), BF16, Ct, npix, c, None, stream())
+            off += c
+        ctx.chans = chans
         return out
 
     @staticmethod
     def backward(ctx, dy):
         if dy.dtype != _BF or dy.stride(1) != 1:
             dy = to_nhwc(dy)
-        return dy[:, :ctx.c1], dy[:, ctx.c1:]
+        outs, off = [], 0
+        for c in ctx.chans:
+            outs.append(dy[:, off:off + c])
+            off += c
+        return tuple(outs)
 
 
 class AddFn(torch.autograd.Function):

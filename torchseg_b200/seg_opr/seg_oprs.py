@@ -34,7 +34,8 @@ def conv_bn_act(x, conv, bn, relu, residual=None):
     """fused conv → norm_layer(train/eval) → (+residual) → ReLU on the libtsb path"""
     ks = conv.kernel_size[0]
     assert conv.kernel_size[0] == conv.kernel_size[1] and conv.groups == 1 and conv.bias is None
-    stem = (conv.in_channels == 3 and ks == 7 and conv.stride[0] == 2 and conv.padding[0] == 3)
+    stem = (conv.in_channels == 3 and conv.stride[0] == 2 and conv.dilation[0] == 1 and
+            (ks, conv.padding[0]) in ((7, 3), (3, 1)))
     if stem:
         xin = _packed_image(x) if x.shape[1] == 3 else x
     else:
