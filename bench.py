@@ -23,9 +23,12 @@ import torch  # noqa: E402
 
 H = W = 1024
 NUM_CLASSES = 19
+IGNORE = 255
 BATCH_PER_GPU = 16
 STEP_GFLOP_PER_IMG = 338.1   # 3 x 116.00 - 2 x 4.933 (conv FLOPs, fprop+dgrad+wgrad)
 METRIC = "images/sec training step (1024x1024, 19-class)"
+MODEL = "bisenet"            # --model pspnet: secondary line for BASELINE configs[2] (PSPNet-R101_v1c d8, ADE shape)
+WORKLOAD = "BiSeNet-R18 train step, 1024x1024, 19-class, OHEM (BASELINE configs[1])"
 
 
 def load_peaks():
@@ -41,7 +44,7 @@ def synth_batch(n, h, w, seed, device="cpu", pin=False):
     g = torch.Generator().manual_seed(seed)
     imgs = torch.randn(n, 3, h, w, generator=g)
     labels = torch.randint(0, NUM_CLASSES, (n, h, w), generator=g, dtype=torch.int64)
-    labels[:, : h // 10, :] = 255  # deterministic ~10 % ignore band
+    labels[:, : h // 10, :] = IGNORE  # deterministic ~10 % ignore band
     if pin and torch.cuda.is_available():
         imgs, labels = imgs.pin_memory(), labels.pin_memory()
     return imgs.to(device), labels.to(device)
@@ -93,6 +96,26 @@ def build_b200(device, world):
     from torchseg_b200.seg_opr.loss_opr import ProbOhemCrossEntropy2d
     from torchseg_b200.utils.init_func import init_weight, group_weight
     norm = SyncBatchNorm if world > 1 else torch.nn.BatchNorm2d
+    if MODEL == "pspnet":
+        # model/pspnet/ade.pspnet.R101_v1c/train.py:47-90: CE(ignore -1), backbone lr, business layers 10x lr
+        from torchseg_b200.networks import PSPNet
+        torch.manual_seed(304)
+        model = PSPNet(NUM_CLASSES, torch.nn.CrossEntropyLoss(reduction='mean', ignore_index=-1), None, norm)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout2d):
+                mod.p = 0.1
+        init_weight(model.business_layer, torch.nn.init.kaiming_normal_, norm, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+        model.to(device)
+        torchseg_b200.prepare_model(model)
+        base_lr = 1e-2
+        groups = group_weight([], model.backbone, norm, base_lr)
+        for m in model.business_layer:
+            groups = group_weight(groups, m, norm, base_lr * 10)
+        opt = optim.SGD(groups, lr=base_lr, momentum=0.9, weight_decay=1e-4)
+        lr_policy = PolyLR(base_lr, 0.9, 120 * 1000)
+        ddp = DistributedDataParallel(model) if world > 1 else None
+        model.train()
+        return model, ddp, opt, lr_policy
     min_kept = BATCH_PER_GPU * H * W // 16  # train.py:48-49
     crit = ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=False)
     torch.manual_seed(12345)
@@ -194,13 +217,16 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ main arm
 def main():
-    global BATCH_PER_GPU
+    global BATCH_PER_GPU, MODEL, H, W, NUM_CLASSES, IGNORE, STEP_GFLOP_PER_IMG, METRIC, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (BASELINE: 16)")
+    ap.add_argument("--model", default="bisenet", choices=["bisenet", "pspnet"],
+                    help="bisenet = BASELINE configs[1] (the metric); pspnet = secondary line for configs[2]")
+    ap.add_argument("--size", type=int, default=0, help="input size override (pspnet default 480, the reference shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -219,6 +245,14 @@ def main():
         dist.init_process_group("nccl", init_method="env://", device_id=device)
     warmup = max(3, args.warmup)
     BATCH_PER_GPU = args.batch
+    if args.model == "pspnet":
+        MODEL, NUM_CLASSES, IGNORE = "pspnet", 150, -1
+        H = W = args.size or 480
+        STEP_GFLOP_PER_IMG = 1588.7 * (H * W) / (480.0 * 480.0)   # BASELINE.md §2 (529.62 GF fwd @480^2)
+        METRIC = "images/sec training step (%dx%d, 150-class)" % (H, W)
+        WORKLOAD = "PSPNet-R101_v1c dilated-8 train step, %dx%d, 150-class CE (BASELINE configs[2] family, reference shape 480)" % (H, W)
+    elif args.size:
+        H = W = args.size
 
     model, ddp, opt, lr_policy = build_b200(device, world)
     host_imgs, host_gts = synth_batch(BATCH_PER_GPU, H, W, 100 + rank, pin=True)
@@ -299,7 +333,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BiSeNet-R18 train step, 1024x1024, 19-class, OHEM (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
                        "sync_bn": world > 1, "optimizer": "fused flat SGD (momentum 0.9, wd 5e-4, poly LR)",
                        "l2_policy": "inputs larger than L2 (activations >> 126 MB per step), no explicit flush",
@@ -319,7 +353,7 @@ def main():
                          "launches": prof["launches"], "kernel_ms_per_step": prof["ms"] / args.steps,
                          "peak_source": peaks["src"]},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and MODEL == "bisenet":
             threads = pick_threads()
             ips, _ = cpu_reference_steps(2, 512, 512, 2, 1, threads)
             line["cpu_baseline"] = {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port",
