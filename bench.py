@@ -45,9 +45,14 @@ def synth_batch(n, h, w, seed, device="cpu", pin=False):
     imgs = torch.randn(n, 3, h, w, generator=g)
     labels = torch.randint(0, NUM_CLASSES, (n, h, w), generator=g, dtype=torch.int64)
     labels[:, : h // 10, :] = IGNORE  # deterministic ~10 % ignore band
+    batch = [imgs, labels]
+    if MODEL == "dfn":   # border labels {0,1,255} (dfn dataloader.py:15-29 produces them with Canny + dilate)
+        edge = (torch.rand(n, h, w, generator=g) < 0.1).to(torch.int64)
+        edge[:, : h // 10, :] = IGNORE
+        batch.append(edge)
     if pin and torch.cuda.is_available():
-        imgs, labels = imgs.pin_memory(), labels.pin_memory()
-    return imgs.to(device), labels.to(device)
+        batch = [t.pin_memory() for t in batch]
+    return tuple(t.to(device) for t in batch)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -116,6 +121,25 @@ def build_b200(device, world):
         ddp = DistributedDataParallel(model) if world > 1 else None
         model.train()
         return model, ddp, opt, lr_policy
+    if MODEL == "dfn":
+        # model/dfn/cityscapes.dfn.R101_v1c/train.py:47-80: CE(ignore 255) + 0.1 * focal, backbone lr, business 10x lr
+        from torchseg_b200.networks import DFN
+        from torchseg_b200.seg_opr.loss_opr import SigmoidFocalLoss
+        torch.manual_seed(12345)
+        model = DFN(NUM_CLASSES, torch.nn.CrossEntropyLoss(reduction='mean', ignore_index=255),
+                    SigmoidFocalLoss(ignore_label=255, gamma=2.0, alpha=0.25), 0.1, None, norm)
+        init_weight(model.business_layer, torch.nn.init.kaiming_normal_, norm, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+        model.to(device)
+        torchseg_b200.prepare_model(model)
+        base_lr = 7e-4
+        groups = group_weight([], model.backbone, norm, base_lr)
+        for m in model.business_layer:
+            groups = group_weight(groups, m, norm, base_lr * 10)
+        opt = optim.SGD(groups, lr=base_lr, momentum=0.9, weight_decay=1e-4)
+        lr_policy = PolyLR(base_lr, 0.9, 80 * 1000)
+        ddp = DistributedDataParallel(model) if world > 1 else None
+        model.train()
+        return model, ddp, opt, lr_policy
     min_kept = BATCH_PER_GPU * H * W // 16  # train.py:48-49
     crit = ProbOhemCrossEntropy2d(ignore_label=255, thresh=0.7, min_kept=min_kept, use_weight=False)
     torch.manual_seed(12345)
@@ -134,9 +158,9 @@ def build_b200(device, world):
     return model, ddp, opt, lr_policy
 
 
-def train_step(model, ddp, opt, lr_policy, it, imgs, gts):
+def train_step(model, ddp, opt, lr_policy, it, *inputs):
     opt.zero_grad()
-    loss = (ddp or model)(imgs, gts)
+    loss = (ddp or model)(*inputs)
     lr = lr_policy.get_lr(it)
     for i, g in enumerate(opt.param_groups):
         g['lr'] = lr if i < 2 else lr * 10  # train.py:136-139
@@ -224,8 +248,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (BASELINE: 16)")
-    ap.add_argument("--model", default="bisenet", choices=["bisenet", "pspnet"],
-                    help="bisenet = BASELINE configs[1] (the metric); pspnet = secondary line for configs[2]")
+    ap.add_argument("--model", default="bisenet", choices=["bisenet", "pspnet", "dfn"],
+                    help="bisenet = BASELINE configs[1] (the metric); pspnet / dfn = secondary lines (SURVEY C3 / C4)")
     ap.add_argument("--size", type=int, default=0, help="input size override (pspnet default 480, the reference shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -251,12 +275,20 @@ def main():
         STEP_GFLOP_PER_IMG = 1588.7 * (H * W) / (480.0 * 480.0)   # BASELINE.md §2 (529.62 GF fwd @480^2)
         METRIC = "images/sec training step (%dx%d, 150-class)" % (H, W)
         WORKLOAD = "PSPNet-R101_v1c dilated-8 train step, %dx%d, 150-class CE (BASELINE configs[2] family, reference shape 480)" % (H, W)
+    elif args.model == "dfn":
+        MODEL = "dfn"
+        H = W = args.size or 1024
+        # 2217.6 GF fwd conv @1024^2; step = 3x - 2x the image-input conv (3->32 3x3/2: 0.453 GF)
+        STEP_GFLOP_PER_IMG = (3 * 2217.6 - 2 * 0.453) * (H * W) / (1024.0 * 1024.0)
+        METRIC = "images/sec training step (%dx%d, 19-class + border)" % (H, W)
+        WORKLOAD = "DFN-R101_v1c train step, %dx%d, 4x CE + 0.1 * 4x focal (SURVEY C4; reference shape 800, 4 img/GPU)" % (H, W)
     elif args.size:
         H = W = args.size
 
     model, ddp, opt, lr_policy = build_b200(device, world)
-    host_imgs, host_gts = synth_batch(BATCH_PER_GPU, H, W, 100 + rank, pin=True)
-    dev_imgs, dev_gts = host_imgs.to(device), host_gts.to(device)
+    host_batch = synth_batch(BATCH_PER_GPU, H, W, 100 + rank, pin=True)
+    dev_batch = tuple(t.to(device) for t in host_batch)
+    keys = ("data", "label", "aux_label")[:len(host_batch)]
 
     def barrier():
         if world > 1:
@@ -271,7 +303,7 @@ def main():
 
     it = 0
     for _ in range(warmup):
-        loss = train_step(model, ddp, opt, lr_policy, it, dev_imgs, dev_gts)
+        loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
         it += 1
     # ---------------- timed region 1: inputs resident in HBM; conv launches bracketed by CUDA events
     ops.conv_prof.enable()
@@ -281,7 +313,7 @@ def main():
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(args.steps):
-            loss = train_step(model, ddp, opt, lr_policy, it, dev_imgs, dev_gts)
+            loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
             it += 1
         e1.record()
         barrier()
@@ -297,21 +329,21 @@ def main():
 
     def host_batches(n):
         for _ in range(n):
-            yield {"data": host_imgs, "label": host_gts}
+            yield dict(zip(keys, host_batch))
 
     loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
     # one untimed e2e step warms the pipeline (device slots allocated, first batch in flight); inside the timed region
     # exactly one H2D batch copy is issued per step (the copy of step i+1 overlaps the compute of step i)
     loader = CudaPrefetcher(host_batches(args.steps + 2), device)
     mb = loader.next()
-    train_step(model, ddp, opt, lr_policy, it, mb["data"], mb["label"])
+    train_step(model, ddp, opt, lr_policy, it, *[mb[k] for k in keys])
     it += 1
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for k in range(args.steps):
         mb = loader.next()                                       # train.py:119-124
-        loss = train_step(model, ddp, opt, lr_policy, it, mb["data"], mb["label"])
+        loss = train_step(model, ddp, opt, lr_policy, it, *[mb[k] for k in keys])
         it += 1
         loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # train.py:146 (per-iteration loss read)
     e3.record()
@@ -341,7 +373,7 @@ def main():
                        "step_conv_gflop_per_img": STEP_GFLOP_PER_IMG,
                        "frac_of_conv_flop_roofline": value / world * STEP_GFLOP_PER_IMG / 1e3 / peaks["tflops"]},
             "e2e": {"value": e2e_v, "unit": "images/sec",
-                    "h2d_bytes_per_step": int(host_imgs.numel() * 4 + host_gts.numel() * 8), "d2h_bytes_per_step": 4,
+                    "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in host_batch)), "d2h_bytes_per_step": 4,
                     "input_pipeline": "pinned host buffers, side-stream prefetch (torchseg_b200.utils.prefetch.CudaPrefetcher)"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),

@@ -198,6 +198,12 @@ int tsb_cast_scale(const void* src, int sdtype, int scs, void* dst, int ddtype, 
 /* y = a + b (bf16 NHWC) */
 int tsb_add(const void* a, int acs, const void* b, int bcs, void* y, int ycs, long long npix, int C,
             tsb_stream_t stream);
+/* y = relu(a + b): the `self.relu(t + x)` tail of RefineResidual / BNRefine (seg_oprs.py:158-162,184-188);
+ * dx = (y > 0) ? dy : 0 is its backward (the same dx goes to both addends) */
+int tsb_add_relu(const void* a, int acs, const void* b, int bcs, void* y, int ycs, long long npix, int C,
+                 tsb_stream_t stream);
+int tsb_relu_bwd(const void* dy, int dycs, const void* y, int ycs, void* dx, int dxcs, long long npix, int C,
+                 tsb_stream_t stream);
 
 /* ================================================================================================
  * Convolution as im2col-free implicit GEMM on tcgen05 tensor cores (TMA → 128B-swizzled smem →

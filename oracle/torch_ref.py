@@ -246,7 +246,7 @@ def bottleneck(x, sd, prefix, stride, dil2, has_down, down_stride, eps, momentum
     return q(F.relu(out + residual))
 
 
-def resnet_v1c_d8(x, sd, prefix, layers, eps, momentum, training, stats=None):
+def resnet_v1c_d8(x, sd, prefix, layers, eps, momentum, training, stats=None, dilated=True):
     """ResNet.forward with deep stem (resnet.py:110-124,168-184) after PSPNet._nostride_dilate(layer3, 2) and
     (layer4, 4) (pspnet network.py:22-23,62-72): stride-2 3x3 → stride 1, dilation=padding=d//2; other 3x3 → d;
     the stride-2 1x1 downsample → stride 1."""
@@ -266,6 +266,8 @@ def resnet_v1c_d8(x, sd, prefix, layers, eps, momentum, training, stats=None):
             if li == 1:
                 stride, dil2, dstride = 1, 1, 1
             elif li == 2:
+                stride, dil2, dstride = (2 if first else 1), 1, 2
+            elif not dilated:  # plain output-stride-32 trunk (DFN, dfn network.py:20-23)
                 stride, dil2, dstride = (2 if first else 1), 1, 2
             elif li == 3:      # dilate = 2
                 stride, dil2, dstride = 1, (1 if first else 2), 1
@@ -299,3 +301,78 @@ def pspnet_loss(data, label, sd, layers=(3, 4, 23, 3), aux_ratio=0.4, ignore_lab
     aux = F.log_softmax(F.interpolate(aux, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
     loss = F.cross_entropy(psp, label, ignore_index=ignore_label)
     return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label), (psp, aux)
+
+
+# --------------------------------------------------------------------------------------------------
+# DFN (model/dfn/cityscapes.dfn.R101_v1c/network.py)
+# --------------------------------------------------------------------------------------------------
+def refine_residual(x, sd, prefix, has_relu, eps, momentum, training, stats=None):
+    """RefineResidual.forward — /root/reference/furnace/seg_opr/seg_oprs.py:182-188"""
+    x = q(F.conv2d(x, qw(sd[prefix + ".conv_1x1.weight"])))
+    t = conv_bn_relu(x, sd, prefix + ".cbr", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
+    t = q(F.conv2d(t, qw(sd[prefix + ".conv_refine.weight"]), None, 1, 1))
+    return q(F.relu(t + x)) if has_relu else q(t + x)
+
+
+def channel_attention(x1, x2, sd, prefix):
+    """ChannelAttention.forward + SELayer.forward — seg_oprs.py:121-126,135-140"""
+    fm = torch.cat([x1, x2], 1)
+    y = q(F.adaptive_avg_pool2d(fm, 1)).flatten(1)
+    y = q(F.relu(q(F.linear(y, qw(sd[prefix + ".channel_attention.fc.0.weight"]), sd[prefix + ".channel_attention.fc.0.bias"]))))
+    y = q(F.linear(y, qw(sd[prefix + ".channel_attention.fc.2.weight"]), sd[prefix + ".channel_attention.fc.2.bias"]))
+    a = torch.sigmoid(y).view(y.shape[0], -1, 1, 1)
+    return q(x1 * a + x2)
+
+
+def dfn_head_logits(x, sd, prefix, eps, momentum, training, stats=None):
+    """DFNHead.forward before the up-sampling — dfn network.py:166-168"""
+    x = refine_residual(x, sd, prefix + ".rrb", False, eps, momentum, training, stats)
+    return F.conv2d(x, qw(sd[prefix + ".conv.weight"]), sd[prefix + ".conv.bias"])
+
+
+def dfn_forward(blocks, sd, eps=1e-5, momentum=0.1, training=True, stats=None):
+    """DFN.forward from the four backbone blocks to the low-resolution head outputs — dfn network.py:95-137.
+    Returns ([4 smooth logits, deepest first], [4 border logits], [4 smooth head inputs], [4 border head inputs])."""
+    deep = blocks[::-1]
+    gc = q(F.adaptive_avg_pool2d(deep[0], 1))
+    gc = conv_bn_relu(gc, sd, "global_context.1", 1, 0, eps=eps, momentum=momentum, training=training, stats=stats)
+    last_fm = q(F.interpolate(gc, size=deep[0].shape[2:], mode="bilinear", align_corners=True))
+    smooth_fm, smooth = [], []
+    for i, fm in enumerate(deep):
+        fm = refine_residual(fm, sd, "smooth_pre_rrbs.%d" % i, True, eps, momentum, training, stats)
+        fm = channel_attention(fm, last_fm, sd, "cabs.%d" % i)
+        fm = refine_residual(fm, sd, "smooth_aft_rrbs.%d" % i, True, eps, momentum, training, stats)
+        smooth_fm.append(fm)
+        smooth.append(dfn_head_logits(fm, sd, "smooth_heads.%d" % i, eps, momentum, training, stats))
+        if i != 3:
+            last_fm = q(F.interpolate(fm, scale_factor=2, mode="bilinear", align_corners=True))
+    last_fm = None
+    border_fm, border = [], []
+    for i, fm in enumerate(blocks):
+        fm = refine_residual(fm, sd, "border_pre_rrbs.%d" % i, True, eps, momentum, training, stats)
+        if last_fm is not None:
+            fm = q(F.interpolate(fm, scale_factor=2 ** i, mode="bilinear", align_corners=True))
+            last_fm = q(last_fm + fm)
+            last_fm = refine_residual(last_fm, sd, "border_aft_rrbs.%d" % i, True, eps, momentum, training, stats)
+        else:
+            last_fm = fm
+        border_fm.append(last_fm)
+        border.append(dfn_head_logits(last_fm, sd, "border_heads.%d" % i, eps, momentum, training, stats))
+    return smooth, border, smooth_fm, border_fm
+
+
+def dfn_loss(data, label, aux_label, sd, layers=(3, 4, 23, 3), alpha=0.1, ignore_label=255, gamma=2.0,
+             focal_alpha=0.25, eps=1e-5, momentum=0.1, stats=None):
+    """DFN.forward training branch — dfn network.py:139-152 with the criteria of dfn train.py:48-52
+    (CrossEntropyLoss(mean, ignore 255) on the 4 smooth heads, SigmoidFocalLoss on the 4 border heads)."""
+    blocks = resnet_v1c_d8(data, sd, "backbone", layers, eps, momentum, True, stats, dilated=False)
+    smooth, border, _, _ = dfn_forward(blocks, sd, eps, momentum, True, stats)
+    loss = 0.0
+    for i, lo in enumerate(smooth):
+        up = F.interpolate(lo, scale_factor=2 ** (5 - i), mode="bilinear", align_corners=True)
+        loss = loss + F.cross_entropy(up, label, ignore_index=ignore_label)
+    aux = 0.0
+    for lo in border:
+        up = F.interpolate(lo, scale_factor=4, mode="bilinear", align_corners=True)
+        aux = aux + sigmoid_focal(up, aux_label, ignore_label, gamma, focal_alpha)
+    return loss + alpha * aux, (smooth, border)

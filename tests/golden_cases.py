@@ -48,3 +48,14 @@ def pspnet_case(N=2, HW=96, seed=4, classes=150):
     x = torch.randn(N, 3, HW, HW, generator=g)
     y = torch.randint(-1, classes, (N, HW, HW), generator=g, dtype=torch.int64)
     return x, y, seed
+
+
+def dfn_case(N=2, HW=128, seed=12345):
+    """BASELINE configs C4 shape family (DFN R101_v1c, Cityscapes 19 classes + {0,1,255} border labels), small size"""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, 3, HW, HW, generator=g)
+    y = torch.randint(0, 19, (N, HW, HW), generator=g, dtype=torch.int64)
+    y[:, : HW // 10, :] = 255
+    e = (torch.rand(N, HW, HW, generator=g) < 0.15).to(torch.int64)
+    e[:, : HW // 10, :] = 255
+    return x, y, e, seed

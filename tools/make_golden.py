@@ -16,7 +16,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
 from oracle import reference_live as rl  # noqa: E402
-from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, OHEM_REGIMES  # noqa: E402
+from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, dfn_case, OHEM_REGIMES  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -101,6 +101,23 @@ def main():
                            "grad_norms": {n: float(p.grad.norm()) for n, p in m.named_parameters()
                                           if n in ("backbone.conv1.0.weight", "backbone.layer3.5.conv2.weight",
                                                    "psp_layer.conv6.0.conv.weight", "aux_layer.2.weight")}}
+
+    # DFN-R101_v1c: CrossEntropyLoss on the smooth heads + 0.1 * SigmoidFocalLoss on the border heads
+    dfn = rl.load_network('dfn/cityscapes.dfn.R101_v1c', num_classes=19)
+    x, y, e, seed = dfn_case()
+    torch.manual_seed(seed)
+    m = dfn.DFN(19, nn.CrossEntropyLoss(reduction='mean', ignore_index=255),
+                lo.SigmoidFocalLoss(ignore_label=255, gamma=2.0, alpha=0.25), 0.1, None, nn.BatchNorm2d)
+    m.train()
+    loss = m(x, y, e)
+    loss.backward()
+    gold["dfn_r101"] = {"loss": float(loss), "n_params": sum(p.numel() for p in m.parameters()),
+                        "n_state": len(m.state_dict()),
+                        "grad_norms": {n: float(p.grad.norm()) for n, p in m.named_parameters()
+                                       if n in ("backbone.conv1.0.weight", "backbone.layer4.2.conv3.weight",
+                                                "smooth_pre_rrbs.0.cbr.conv.weight", "cabs.3.channel_attention.fc.0.weight",
+                                                "border_aft_rrbs.3.conv_refine.weight", "smooth_heads.3.conv.weight",
+                                                "border_heads.0.conv.bias")}}
 
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "reference_outputs.json"), "w") as f:

@@ -56,6 +56,8 @@ _SIGS = {
     "tsb_unpack_stem_wgrad": [P, I, I, P, P],
     "tsb_cast_scale": [P, I, I, P, I, I, L, I, P, P],
     "tsb_add": [P, I, P, I, P, I, L, I, P],
+    "tsb_add_relu": [P, I, P, I, P, I, L, I, P],
+    "tsb_relu_bwd": [P, I, P, I, P, I, L, I, P],
     "tsb_conv2d_fprop": [P, P, I, P, P, P, I, I, P, P, P],
     "tsb_conv2d_dgrad": [P, P, I, P, P, I, I, P],
     "tsb_conv2d_wgrad": [P, P, I, P, I, P, P],

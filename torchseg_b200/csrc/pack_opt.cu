@@ -116,6 +116,40 @@ add_kernel(const __nv_bfloat16* __restrict__ a, int acs, const __nv_bfloat16* __
     }
 }
 
+// y = relu(a + b): tail of RefineResidual / BNRefine (seg_oprs.py:158-162,184-188)
+__global__ void __launch_bounds__(kThreads)
+add_relu_kernel(const __nv_bfloat16* __restrict__ a, int acs, const __nv_bfloat16* __restrict__ b, int bcs,
+                __nv_bfloat16* __restrict__ y, int ycs, long long npix, int C8) {
+    const long long total = npix * C8;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        int c8 = (int)(i % C8);
+        long long p = i / C8;
+        float u[8], v[8];
+        Vec8<__nv_bfloat16>::load(a + p * acs + c8 * 8, u);
+        Vec8<__nv_bfloat16>::load(b + p * bcs + c8 * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = fmaxf(u[k] + v[k], 0.f);
+        Vec8<__nv_bfloat16>::store(y + p * ycs + c8 * 8, u);
+    }
+}
+
+// dx = (y > 0) ? dy : 0
+__global__ void __launch_bounds__(kThreads)
+relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ y, int ycs,
+                __nv_bfloat16* __restrict__ dx, int dxcs, long long npix, int C8) {
+    const long long total = npix * C8;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+        int c8 = (int)(i % C8);
+        long long p = i / C8;
+        float u[8], v[8];
+        Vec8<__nv_bfloat16>::load(dy + p * dycs + c8 * 8, u);
+        Vec8<__nv_bfloat16>::load(y + p * ycs + c8 * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = v[k] > 0.f ? u[k] : 0.f;
+        Vec8<__nv_bfloat16>::store(dx + p * dxcs + c8 * 8, u);
+    }
+}
+
 // db[k] += Σ_pix dy[pix,k]; one warp per pixel stripe, lanes over channels (K <= 64 typical: 19 padded)
 __global__ void __launch_bounds__(kThreads)
 bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, long long npix, int K, float* __restrict__ db) {
@@ -269,6 +303,28 @@ extern "C" int tsb_add(const void* a, int acs, const void* b, int bcs, void* y, 
     int grid = tsb_grid_for(npix * C8, kThreads, 8);
     add_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, acs, (const __nv_bfloat16*)b, bcs, (__nv_bfloat16*)y, ycs, npix, C8);
     TSB_CUDA_CHECK_LAUNCH("add");
+    return TSB_OK;
+}
+
+extern "C" int tsb_add_relu(const void* a, int acs, const void* b, int bcs, void* y, int ycs, long long npix, int C,
+                            tsb_stream_t stream) {
+    TSB_REQUIRE(a && b && y && npix > 0, "tsb_add_relu: bad args");
+    TSB_REQUIRE(C % 8 == 0 && acs % 8 == 0 && bcs % 8 == 0 && ycs % 8 == 0, "tsb_add_relu: alignment");
+    int C8 = C / 8;
+    int grid = tsb_grid_for(npix * C8, kThreads, 8);
+    add_relu_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, acs, (const __nv_bfloat16*)b, bcs, (__nv_bfloat16*)y, ycs, npix, C8);
+    TSB_CUDA_CHECK_LAUNCH("add_relu");
+    return TSB_OK;
+}
+
+extern "C" int tsb_relu_bwd(const void* dy, int dycs, const void* y, int ycs, void* dx, int dxcs, long long npix, int C,
+                            tsb_stream_t stream) {
+    TSB_REQUIRE(dy && y && dx && npix > 0, "tsb_relu_bwd: bad args");
+    TSB_REQUIRE(C % 8 == 0 && dycs % 8 == 0 && ycs % 8 == 0 && dxcs % 8 == 0, "tsb_relu_bwd: alignment");
+    int C8 = C / 8;
+    int grid = tsb_grid_for(npix * C8, kThreads, 8);
+    relu_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, dycs, (const __nv_bfloat16*)y, ycs, (__nv_bfloat16*)dx, dxcs, npix, C8);
+    TSB_CUDA_CHECK_LAUNCH("relu_bwd");
     return TSB_OK;
 }
 

@@ -5,6 +5,7 @@ App. D) depend on that — only `forward` is replaced by the fused libtsb path.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import ops
 
@@ -30,6 +31,38 @@ def _packed_image(img):
     return packed
 
 
+def _ceil_to(n, m):
+    return (n + m - 1) // m * m
+
+
+def _pad_weight(w, Kp, Cp):
+    """zero-pad a KRSC-backed [K,C,R,S] weight to [Kp,Cp,R,S] (autograd slices the gradient back)"""
+    K, C = w.shape[:2]
+    if K == Kp and C == Cp:
+        return w
+    wk = F.pad(w.permute(0, 2, 3, 1), (0, Cp - C, 0, 0, 0, 0, 0, Kp - K))
+    return wk.permute(0, 3, 1, 2)
+
+
+def _pad_vec(v, Kp, value=0.0):
+    return v if v.shape[0] == Kp else F.pad(v, (0, Kp - v.shape[0]), value=value)
+
+
+def _pad_act(x, Cp):
+    """activation with a ragged channel count arriving from outside the padded domain: copy into zero pads"""
+    N, C, H, W = x.shape
+    out = ops.nhwc_zeros(N, Cp, H, W, device=x.device)
+    out[:, :C].copy_(x)
+    return out
+
+
+def _ragged(conv, x):
+    """DFN's 21 / 171 / 9-channel layers (dfn network.py:58-72,160-164): the tensor-core kernels tile GEMM-K in
+    64-channel boxes, so these layers run zero-padded to the next multiple of 64. Pad channels carry exact zeros
+    through conv (zero weight rows/columns), BN (beta pad 0) and ReLU, forward and backward."""
+    return conv.in_channels != x.shape[1] or conv.in_channels % 64 != 0
+
+
 def conv_bn_act(x, conv, bn, relu, residual=None):
     """fused conv → norm_layer(train/eval) → (+residual) → ReLU on the libtsb path"""
     ks = conv.kernel_size[0]
@@ -43,14 +76,42 @@ def conv_bn_act(x, conv, bn, relu, residual=None):
     if residual is not None:
         residual = _as_act(residual)
     momentum = bn.momentum if bn.momentum is not None else 0.1
-    return ops.ConvBNActFn.apply(xin, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var,
-                                 conv.stride[0], conv.padding[0], conv.dilation[0], bool(relu), float(bn.eps),
-                                 float(momentum), bool(bn.training), stem)
+    w, gamma, beta, rm, rv = conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var
+    K = conv.out_channels
+    padded = (not stem) and (_ragged(conv, xin) or K % 64 != 0)
+    if padded:
+        Cp, Kp = _ceil_to(xin.shape[1], 64), _ceil_to(K, 64)
+        if xin.shape[1] != Cp:
+            xin = _pad_act(xin, Cp)
+        w = _pad_weight(w, Kp, Cp)
+        gamma, beta = _pad_vec(gamma, Kp, 1.0), _pad_vec(beta, Kp)
+        with torch.no_grad():
+            rm, rv = _pad_vec(rm, Kp), _pad_vec(rv, Kp, 1.0)
+    y = ops.ConvBNActFn.apply(xin, w, gamma, beta, residual, rm, rv,
+                              conv.stride[0], conv.padding[0], conv.dilation[0], bool(relu), float(bn.eps),
+                              float(momentum), bool(bn.training), stem)
+    if padded and bn.training and rm is not bn.running_mean:
+        with torch.no_grad():
+            bn.running_mean.copy_(rm[:K])
+            bn.running_var.copy_(rv[:K])
+    return y
 
 
-def conv_plain(x, conv, out_f32=False, ocs=None):
-    return ops.ConvFn.apply(_as_act(x), conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0],
-                            bool(out_f32), ocs)
+def conv_plain(x, conv, out_f32=False, ocs=None, pad_out=False):
+    """nn.Conv2d (+bias) on the libtsb path. pad_out: keep the output in the 64-padded channel domain (DFN's
+    BN-free 1x1 / refine convs); otherwise the output has exactly conv.out_channels channels (classifiers)."""
+    xin = _as_act(x)
+    w, b = conv.weight, conv.bias
+    K = conv.out_channels
+    if _ragged(conv, xin) or (pad_out and K % 64 != 0):
+        Cp = _ceil_to(xin.shape[1], 64)
+        Kp = _ceil_to(K, 64) if pad_out else K
+        if xin.shape[1] != Cp:
+            xin = _pad_act(xin, Cp)
+        w = _pad_weight(w, Kp, Cp)
+        if b is not None:
+            b = _pad_vec(b, Kp)
+    return ops.ConvFn.apply(xin, w, b, conv.stride[0], conv.padding[0], conv.dilation[0], bool(out_f32), ocs)
 
 
 class ConvBnRelu(nn.Module):
@@ -142,6 +203,124 @@ class FeatureFusion(nn.Module):
         pooled = ops.AdaptiveAvgPoolFn.apply(fm, 1)
         a = self.channel_attention[2](self.channel_attention[1](pooled))
         return ops.ChanScaleFn.apply(fm, a, None, 1.0)
+
+
+class AddReluFn(torch.autograd.Function):
+    """relu(a + b) in one pass (tsb_add_relu); the backward mask comes from the saved output"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        N, C, H, W = a.shape
+        y = ops.nhwc_empty(N, C, H, W, device=a.device)
+        ops.call("tsb_add_relu", ops.ptr(a), ops.cs_of(a), ops.ptr(b), ops.cs_of(b), ops.ptr(y), C, N * H * W, C,
+                 ops.stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        N, C, H, W = y.shape
+        if dy.dtype != torch.bfloat16 or dy.stride(1) != 1:
+            dy = ops.to_nhwc(dy)
+        dx = ops.nhwc_empty(N, C, H, W, device=y.device)
+        ops.call("tsb_relu_bwd", ops.ptr(dy), ops.cs_of(dy), ops.ptr(y), C, ops.ptr(dx), C, N * H * W, C, ops.stream())
+        return dx, dx
+
+
+def _residual_tail(t, x, has_relu):
+    return AddReluFn.apply(t, x) if has_relu else ops.AddFn.apply(t, x)
+
+
+class SELayer(nn.Module):
+    """seg_oprs.py:110-126 — GAP → Linear → ReLU → Linear → Sigmoid. The two nn.Linear layers keep their names
+    (fc.0 / fc.2, checkpoint keys) and run as 1x1 convolutions over the [N,C,1,1] pooled tensor."""
+
+    def __init__(self, in_planes, out_planes, reduction=16):
+        super(SELayer, self).__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(
+            nn.Linear(in_planes, out_planes // reduction),
+            nn.ReLU(inplace=True),
+            nn.Linear(out_planes // reduction, out_planes),
+            nn.Sigmoid())
+        self.out_planes = out_planes
+
+    @staticmethod
+    def _linear(y, lin):
+        K, C = lin.weight.shape
+        return ops.ConvFn.apply(y, lin.weight.view(K, C, 1, 1), lin.bias, 1, 0, 1, False, None)
+
+    def logits_from_pooled(self, pooled):
+        """pre-sigmoid attention logit [N,out,1,1] from the pooled [N,in,1,1] descriptor"""
+        y = self._linear(pooled, self.fc[0])
+        y = ReluFn.apply(y)
+        return self._linear(y, self.fc[2])
+
+    def forward(self, x):
+        pooled = ops.AdaptiveAvgPoolFn.apply(_as_act(x), 1)
+        return torch.sigmoid(self.logits_from_pooled(pooled).float())
+
+
+class ChannelAttention(nn.Module):
+    """seg_oprs.py:129-140 (DFN's CAB): fm = x1 * SE(cat[x1, x2]) + x2. GAP(cat[x1,x2]) = cat[GAP(x1), GAP(x2)], so
+    the 2C-channel concatenation is never materialised; sigmoid, scale and `+ x2` are one kernel."""
+
+    def __init__(self, in_planes, out_planes, reduction):
+        super(ChannelAttention, self).__init__()
+        self.channel_attention = SELayer(in_planes, out_planes, reduction)
+
+    def forward(self, x1, x2):
+        x1, x2 = _as_act(x1), _as_act(x2)
+        pooled = ops.ConcatFn.apply(ops.AdaptiveAvgPoolFn.apply(x1, 1), ops.AdaptiveAvgPoolFn.apply(x2, 1))
+        a = self.channel_attention.logits_from_pooled(pooled)
+        return ops.ChanScaleFn.apply(x1, a, x2, 0.0)
+
+
+class BNRefine(nn.Module):
+    """seg_oprs.py:143-162"""
+
+    def __init__(self, in_planes, out_planes, ksize, has_bias=False, has_relu=False, norm_layer=nn.BatchNorm2d,
+                 bn_eps=1e-5):
+        super(BNRefine, self).__init__()
+        self.conv_bn_relu = ConvBnRelu(in_planes, out_planes, ksize, 1, ksize // 2, has_bias=has_bias,
+                                       norm_layer=norm_layer, bn_eps=bn_eps)
+        self.conv_refine = nn.Conv2d(out_planes, out_planes, kernel_size=ksize, stride=1, padding=ksize // 2,
+                                     dilation=1, bias=has_bias)
+        self.has_relu = has_relu
+        if self.has_relu:
+            self.relu = nn.ReLU(inplace=False)
+
+    def forward(self, x):
+        x = _as_act(x)
+        t = self.conv_bn_relu(x)
+        t = conv_plain(t, self.conv_refine, pad_out=True)
+        if x.shape[1] != t.shape[1]:
+            x = _pad_act(x, t.shape[1])
+        return _residual_tail(t, x, self.has_relu)
+
+
+class RefineResidual(nn.Module):
+    """seg_oprs.py:165-188 (DFN's RRB): x = conv1x1(x); relu?(conv3x3(CBR3x3(x)) + x)"""
+
+    def __init__(self, in_planes, out_planes, ksize, has_bias=False, has_relu=False, norm_layer=nn.BatchNorm2d,
+                 bn_eps=1e-5):
+        super(RefineResidual, self).__init__()
+        self.conv_1x1 = nn.Conv2d(in_planes, out_planes, kernel_size=1, stride=1, padding=0, dilation=1,
+                                  bias=has_bias)
+        self.cbr = ConvBnRelu(out_planes, out_planes, ksize, 1, ksize // 2, has_bias=has_bias,
+                              norm_layer=norm_layer, bn_eps=bn_eps)
+        self.conv_refine = nn.Conv2d(out_planes, out_planes, kernel_size=ksize, stride=1, padding=ksize // 2,
+                                     dilation=1, bias=has_bias)
+        self.has_relu = has_relu
+        if self.has_relu:
+            self.relu = nn.ReLU(inplace=False)
+
+    def forward(self, x):
+        x = conv_plain(x, self.conv_1x1, pad_out=True)
+        t = self.cbr(x)
+        t = conv_plain(t, self.conv_refine, pad_out=True)
+        return _residual_tail(t, x, self.has_relu)
 
 
 class GlobalAvgPool2d(nn.Module):
