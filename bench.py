@@ -101,9 +101,11 @@ def build_b200(device, world):
     from torchseg_b200.seg_opr.loss_opr import ProbOhemCrossEntropy2d
     from torchseg_b200.utils.init_func import init_weight, group_weight
     norm = SyncBatchNorm if world > 1 else torch.nn.BatchNorm2d
-    if MODEL == "pspnet":
-        # model/pspnet/ade.pspnet.R101_v1c/train.py:47-90: CE(ignore -1), backbone lr, business layers 10x lr
-        from torchseg_b200.networks import PSPNet
+    if MODEL in ("pspnet", "psanet"):
+        # model/{pspnet,psanet}/ade.*.R101_v1c/train.py:47-90: CE(ignore -1), backbone lr, business layers 10x lr
+        from torchseg_b200.networks import PSPNet, PSANet
+        if MODEL == "psanet":
+            PSPNet = PSANet
         torch.manual_seed(304)
         model = PSPNet(NUM_CLASSES, torch.nn.CrossEntropyLoss(reduction='mean', ignore_index=-1), None, norm)
         for mod in model.modules():
@@ -248,7 +250,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="per-GPU batch (BASELINE: 16)")
-    ap.add_argument("--model", default="bisenet", choices=["bisenet", "pspnet", "dfn"],
+    ap.add_argument("--model", default="bisenet", choices=["bisenet", "pspnet", "psanet", "dfn"],
                     help="bisenet = BASELINE configs[1] (the metric); pspnet / dfn = secondary lines (SURVEY C3 / C4)")
     ap.add_argument("--size", type=int, default=0, help="input size override (pspnet default 480, the reference shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -275,6 +277,12 @@ def main():
         STEP_GFLOP_PER_IMG = 1588.7 * (H * W) / (480.0 * 480.0)   # BASELINE.md §2 (529.62 GF fwd @480^2)
         METRIC = "images/sec training step (%dx%d, 150-class)" % (H, W)
         WORKLOAD = "PSPNet-R101_v1c dilated-8 train step, %dx%d, 150-class CE (BASELINE configs[2] family, reference shape 480)" % (H, W)
+    elif args.model == "psanet":
+        MODEL, NUM_CLASSES, IGNORE = "psanet", 150, -1
+        H = W = 480    # the PSA head needs exactly 60x60 = 3600 positions (psanet network.py:88)
+        STEP_GFLOP_PER_IMG = 3 * (590.03 + 26.5) - 2 * 0.10    # conv 590.03 GF + bmm 26.5 GF fwd @480^2
+        METRIC = "images/sec training step (480x480, 150-class)"
+        WORKLOAD = "PSANet-R101_v1c dilated-8 train step, 480x480, 150-class CE (SURVEY C5); conv + PSA bmm FLOPs"
     elif args.model == "dfn":
         MODEL = "dfn"
         H = W = args.size or 1024
@@ -356,10 +364,14 @@ def main():
         n_img = BATCH_PER_GPU * world * args.steps
         value = n_img / (ms / 1000.0)
         e2e_v = n_img / (ms_e2e / 1000.0)
-        conv_tf = prof["flops"] / max(prof["ms"], 1e-9) / 1e9  # TFLOP/s over all conv launches of the region
+        # ALGORITHMIC conv FLOPs of the step (SURVEY §8d figure x images of this rank) over the measured duration of all
+        # conv launches of the region. prof["flops"] counts the launched shapes, which include the zero-padded
+        # channels of DFN's ragged layers (and is identical to the algorithmic figure for BiSeNet / PSPNet).
+        algo_flops = STEP_GFLOP_PER_IMG * 1e9 * BATCH_PER_GPU * args.steps
+        conv_tf = min(prof["flops"], algo_flops) / max(prof["ms"], 1e-9) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-        if os.path.exists(tpath):  # DRAM bytes of the same launches from the committed ncu pass (per step)
+        if os.path.exists(tpath) and MODEL == "bisenet":  # DRAM bytes of the same launches from the committed ncu pass (per step)
             traffic = json.load(open(tpath)).get("conv_dram_bytes_per_step")
         line = {
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
@@ -367,7 +379,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * world, "parallelism": "dp%d" % world,
-                       "sync_bn": world > 1, "optimizer": "fused flat SGD (momentum 0.9, wd 5e-4, poly LR)",
+                       "sync_bn": world > 1, "optimizer": "fused flat SGD (momentum 0.9, poly LR, reference wd / lr groups)",
                        "l2_policy": "inputs larger than L2 (activations >> 126 MB per step), no explicit flush",
                        "final_loss": final_loss,
                        "step_conv_gflop_per_img": STEP_GFLOP_PER_IMG,
@@ -380,7 +392,8 @@ def main():
             "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": conv_tf / peaks["tflops"], "traffic": traffic,
                          "traffic_note": "dram__bytes_read+write summed over the conv launches of ONE step (profiles/r01_conv_traffic.json); algorithmic minimum ~5.9 GB/step",
-                         "flops_per_step": prof["flops"] / args.steps,
+                         "flops_per_step": min(prof["flops"], algo_flops) / args.steps,
+                         "launched_flops_per_step": prof["flops"] / args.steps,
                          "kernel": "tcgen05 implicit-GEMM conv kernels (igemm_v2_kernel fprop/dgrad/stem + wgrad_rows_kernel/wgrad_mnmajor_kernel), all launches of the step",
                          "launches": prof["launches"], "kernel_ms_per_step": prof["ms"] / args.steps,
                          "peak_source": peaks["src"]},

@@ -205,6 +205,21 @@ int tsb_add_relu(const void* a, int acs, const void* b, int bcs, void* y, int yc
 int tsb_relu_bwd(const void* dy, int dycs, const void* y, int ycs, void* dx, int dxcs, long long npix, int C,
                  tsb_stream_t stream);
 
+/* ---- point-wise spatial attention (PSANet: model/psanet/ade.psanet.R101_v1c/network.py:119-138) ----
+ * `torch.softmax(att.view(b, c, -1), dim=1)`: in NHWC the softmax runs over the C (=3600) contiguous channels of each
+ * of the `rows` pixels; channels [C, Cp) of the output are written as zeros so the matrix can be the GEMM-K operand
+ * of a 64-channel-tiled 1x1 convolution (input bf16 or fp32 logits: the reference keeps them in fp32 and a peaky
+ * soft-max amplifies bf16 logit rounding). bwd: dA = S * (dS - Σ_c S·dS).
+ * `torch.bmm(reduce_x.view(b,512,-1), S)` itself runs per image on tsb_conv2d_{fprop,dgrad,wgrad} with the image's
+ * feature map as the weight operand; tsb_transpose_pad builds that operand: out[c, r] = in[r, c] (bf16 out, rows of
+ * length ocs, columns [R, Rp) zero-filled). */
+int tsb_softmax_rows_fwd(const void* in, int idtype, int ics, void* out_bf16, int ocs, long long rows, int C, int Cp,
+                         tsb_stream_t stream);
+int tsb_softmax_rows_bwd(const void* S_bf16, int scs, const void* dS_bf16, int dscs, void* dA_bf16, int dacs,
+                         long long rows, int C, int Cp, tsb_stream_t stream);
+int tsb_transpose_pad(const void* in, int idtype, int ics, void* out_bf16, int ocs, int R, int Cc, int Rp,
+                      tsb_stream_t stream);
+
 /* ================================================================================================
  * Convolution as im2col-free implicit GEMM on tcgen05 tensor cores (TMA → 128B-swizzled smem →
  * tcgen05.mma, fp32 accumulators in TMEM) — replaces nn.Conv2d inside ConvBnRelu (seg_oprs.py:29-31),

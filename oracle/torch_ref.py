@@ -376,3 +376,43 @@ def dfn_loss(data, label, aux_label, sd, layers=(3, 4, 23, 3), alpha=0.1, ignore
         up = F.interpolate(lo, scale_factor=4, mode="bilinear", align_corners=True)
         aux = aux + sigmoid_focal(up, aux_label, ignore_label, gamma, focal_alpha)
     return loss + alpha * aux, (smooth, border)
+
+
+# --------------------------------------------------------------------------------------------------
+# PSANet (model/psanet/ade.psanet.R101_v1c/network.py)
+# --------------------------------------------------------------------------------------------------
+def psa_branch(x, sd, prefix, which, eps, momentum, training, stats=None):
+    """one of the two attention branches of PointwiseSpatialAttention.forward — psanet network.py:120-138:
+    reduce = CBR1x1(x); att = conv1x1(CBR1x1(reduce)); bmm(reduce.view(b,512,-1), softmax(att.view(b,c,-1), dim=1))"""
+    red = conv_bn_relu(x, sd, "%s.%s_reduction" % (prefix, which), 1, 0, eps=eps, momentum=momentum, training=training,
+                       stats=stats)
+    att = conv_bn_relu(red, sd, "%s.%s_attention.0" % (prefix, which), 1, 0, eps=eps, momentum=momentum,
+                       training=training, stats=stats)
+    att = F.conv2d(att, qw(sd["%s.%s_attention.1.conv.weight" % (prefix, which)]))   # fp32 logits on both sides
+    b, c, h, w = att.shape
+    S = q(torch.softmax(att.view(b, c, -1), dim=1))
+    fm = torch.bmm(red.view(b, red.shape[1], -1), S)
+    return q(fm.view(b, red.shape[1], h, w))
+
+
+def psa_logits(x, sd, prefix, eps, momentum, training, stats=None):
+    """PointwiseSpatialAttention.forward — psanet network.py:119-144 (Dropout2d disabled in the parity runs)"""
+    collect = psa_branch(x, sd, prefix, "collect", eps, momentum, training, stats)
+    distribute = psa_branch(x, sd, prefix, "distribute", eps, momentum, training, stats)
+    psa = conv_bn_relu(torch.cat([collect, distribute], 1), sd, prefix + ".proj", 1, 0, eps=eps, momentum=momentum,
+                       training=training, stats=stats)
+    fm = torch.cat([x, psa], 1)
+    fm = conv_bn_relu(fm, sd, prefix + ".conv6.0", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
+    return F.conv2d(fm, qw(sd[prefix + ".conv6.2.weight"]), sd[prefix + ".conv6.2.bias"])
+
+
+def psanet_loss(data, label, sd, layers=(3, 4, 23, 3), aux_ratio=0.4, ignore_label=-1, eps=1e-5, momentum=0.1, stats=None):
+    """PSANet (`PSPNet` in psanet network.py) training branch — network.py:41-57"""
+    blocks = resnet_v1c_d8(data, sd, "backbone", layers, eps, momentum, True, stats)
+    psa = psa_logits(blocks[-1], sd, "psa_layer", eps, momentum, True, stats=stats)
+    aux = conv_bn_relu(blocks[-2], sd, "aux_layer.0", 1, 1, eps=eps, momentum=momentum, training=True, stats=stats)
+    aux = F.conv2d(aux, qw(sd["aux_layer.2.weight"]), sd["aux_layer.2.bias"])
+    psa = F.log_softmax(F.interpolate(psa, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+    aux = F.log_softmax(F.interpolate(aux, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+    loss = F.cross_entropy(psa, label, ignore_index=ignore_label)
+    return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label), (psa, aux)

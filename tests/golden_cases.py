@@ -59,3 +59,12 @@ def dfn_case(N=2, HW=128, seed=12345):
     e = (torch.rand(N, HW, HW, generator=g) < 0.15).to(torch.int64)
     e[:, : HW // 10, :] = 255
     return x, y, e, seed
+
+
+def psanet_case(N=1, HW=480, seed=304, classes=150):
+    """SURVEY C5 (PSANet R101_v1c dilated-8, ADE 150 classes, ignore -1). The PSA head needs h*w = 3600 positions at
+    1/8 resolution, so the spatial size cannot be reduced below the reference's 480x480 (psanet config.py)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, 3, HW, HW, generator=g)
+    y = torch.randint(-1, classes, (N, HW, HW), generator=g, dtype=torch.int64)
+    return x, y, seed

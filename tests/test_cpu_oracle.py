@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, dfn_case, OHEM_REGIMES
+from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, dfn_case, psanet_case, OHEM_REGIMES
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "reference_outputs.json")))
@@ -137,6 +137,27 @@ def test_torch_oracle_dfn_vs_golden():
         if v.is_floating_point() and "running" not in k:
             v.requires_grad_(True)
     loss, _ = torch_ref.dfn_loss(x, y, e, sd)
+    assert abs(float(loss) - g["loss"]) < 1e-5 * g["loss"]
+    loss.backward()
+    for n, ref in g["grad_norms"].items():
+        assert abs(float(sd[n].grad.norm()) - ref) < 1e-4 * ref, n
+
+
+def test_torch_oracle_psanet_vs_golden():
+    """PSANet-R101_v1c: construction parity (79.58 M params, 684 state entries) and the oracle restatement
+    of PointwiseSpatialAttention (softmax over the 3600 attention channels + bmm) against the live reference"""
+    from oracle import torch_ref
+    from torchseg_b200.networks import PSANet
+    x, y, seed = psanet_case()
+    torch.manual_seed(seed)
+    m = PSANet(150, torch.nn.CrossEntropyLoss(ignore_index=-1))
+    g = GOLD["psanet_r101"]
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert sum(p.numel() for p in m.parameters()) == g["n_params"] and len(sd) == g["n_state"]
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    loss, _ = torch_ref.psanet_loss(x, y, sd)
     assert abs(float(loss) - g["loss"]) < 1e-5 * g["loss"]
     loss.backward()
     for n, ref in g["grad_norms"].items():

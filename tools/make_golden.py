@@ -16,7 +16,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
 from oracle import reference_live as rl  # noqa: E402
-from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, dfn_case, OHEM_REGIMES  # noqa: E402
+from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, dfn_case, psanet_case, OHEM_REGIMES  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -118,6 +118,25 @@ def main():
                                                 "smooth_pre_rrbs.0.cbr.conv.weight", "cabs.3.channel_attention.fc.0.weight",
                                                 "border_aft_rrbs.3.conv_refine.weight", "smooth_heads.3.conv.weight",
                                                 "border_heads.0.conv.bias")}}
+
+    # PSANet-R101_v1c (the class is called PSPNet in psanet network.py), Dropout2d disabled
+    psa = rl.load_network('psanet/ade.psanet.R101_v1c', num_classes=150)
+    x, y, seed = psanet_case()
+    torch.manual_seed(seed)
+    m = psa.PSPNet(150, nn.CrossEntropyLoss(reduction='mean', ignore_index=-1), None, nn.BatchNorm2d)
+    for mod in m.modules():
+        if isinstance(mod, nn.Dropout2d):
+            mod.p = 0.0
+    m.train()
+    loss = m(x, y)
+    loss.backward()
+    gold["psanet_r101"] = {"loss": float(loss), "n_params": sum(p.numel() for p in m.parameters()),
+                           "n_state": len(m.state_dict()),
+                           "grad_norms": {n: float(p.grad.norm()) for n, p in m.named_parameters()
+                                          if n in ("backbone.layer4.2.conv3.weight",
+                                                   "psa_layer.collect_attention.1.conv.weight",
+                                                   "psa_layer.distribute_reduction.conv.weight",
+                                                   "psa_layer.proj.conv.weight", "psa_layer.conv6.2.weight")}}
 
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "reference_outputs.json"), "w") as f:

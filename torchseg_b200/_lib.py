@@ -57,6 +57,9 @@ _SIGS = {
     "tsb_cast_scale": [P, I, I, P, I, I, L, I, P, P],
     "tsb_add": [P, I, P, I, P, I, L, I, P],
     "tsb_add_relu": [P, I, P, I, P, I, L, I, P],
+    "tsb_softmax_rows_fwd": [P, I, I, P, I, L, I, I, P],
+    "tsb_softmax_rows_bwd": [P, I, P, I, P, I, L, I, I, P],
+    "tsb_transpose_pad": [P, I, I, P, I, I, I, I, P],
     "tsb_relu_bwd": [P, I, P, I, P, I, L, I, P],
     "tsb_conv2d_fprop": [P, P, I, P, P, P, I, I, P, P, P],
     "tsb_conv2d_dgrad": [P, P, I, P, P, I, I, P],

@@ -32,6 +32,14 @@ static inline PFN_encodeTiled get_encode() {
             q == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<PFN_encodeTiled>(f);
     });
+    // The encode call goes to the DRIVER API, which needs a context current on the calling thread. A fresh thread
+    // (autograd's backward worker) that has not yet made a context-binding runtime call gets CUDA_ERROR_INVALID_CONTEXT
+    // (201); cudaFree(0) binds the device's primary context to this thread once.
+    static thread_local bool t_bound = false;
+    if (!t_bound) {
+        cudaFree(0);
+        t_bound = true;
+    }
     return fn;
 }
 

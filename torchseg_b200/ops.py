@@ -689,6 +689,57 @@ class AddFn(torch.autograd.Function):
         return dy, dy
 
 
+class PSABmmFn(torch.autograd.Function):
+    """out = bmm(x.view(b,c,-1), softmax(att.view(b,L,-1), dim=1)) with L = h*w attention channels per pixel
+    (PointwiseSpatialAttention.forward, psanet network.py:122-126,131-138).
+
+    NHWC form per image: out[j, ch] = Σ_i S[j, i] · x[i, ch] with S = row-softmax of att[j, :]. That is a 1x1
+    convolution whose "image" is S (L pixels x L channels, zero-padded to a multiple of 64 channels) and whose weight
+    operand is the image's own feature map transposed ([c, L]); dS is the matching dgrad (weight operand = x itself),
+    dx the matching wgrad. All three run on the tcgen05 conv kernels, one launch per image."""
+
+    @staticmethod
+    def forward(ctx, x, att):
+        b, c, h, w = x.shape
+        L = att.shape[1]
+        assert L == h * w and att.shape[0] == b and tuple(att.shape[2:]) == (h, w), "PSA needs h*w attention channels"
+        assert c % 64 == 0 and L % 8 == 0
+        dev = x.device
+        if cs_of(x) != c:
+            x = to_nhwc(x)
+        Lp = (L + 63) // 64 * 64
+        S = nhwc_empty(b, Lp, h, w, device=dev)
+        call("tsb_softmax_rows_fwd", ptr(att), _lib.dt(att), cs_of(att), ptr(S), Lp, b * h * w, L, Lp, stream())
+        out = nhwc_empty(b, c, h, w, device=dev)
+        xt = torch.empty((c, Lp), dtype=_BF, device=dev)
+        for n in range(b):
+            call("tsb_transpose_pad", ptr(x[n:n + 1]), BF16, c, ptr(xt), Lp, L, c, Lp, stream())
+            conv_fprop(S[n:n + 1], xt, c, 1, 1, 0, 1, out=out[n:n + 1])
+        ctx.save_for_backward(x, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, S = ctx.saved_tensors
+        b, c, h, w = x.shape
+        Lp = S.shape[1]
+        L = h * w
+        dev = x.device
+        if dout.dtype != _BF or dout.stride(1) != 1:
+            dout = to_nhwc(dout)
+        dS = nhwc_empty(b, L, h, w, device=dev, cs=Lp)
+        dx = nhwc_empty(b, c, h, w, device=dev)
+        dxt = torch.empty((c, Lp), dtype=torch.float32, device=dev)
+        for n in range(b):
+            conv_dgrad(dout[n:n + 1], x[n:n + 1], (1, L, h, w), c, 1, 1, 0, 1, out=dS[n:n + 1])
+            dxt.zero_()
+            conv_wgrad(S[n:n + 1], dout[n:n + 1], c, 1, 1, 0, 1, dxt)
+            call("tsb_transpose_pad", ptr(dxt), F32, Lp, ptr(dx[n:n + 1]), c, c, L, c, stream())
+        dA = nhwc_empty(b, L, h, w, device=dev, cs=Lp)
+        call("tsb_softmax_rows_bwd", ptr(S), Lp, ptr(dS), Lp, ptr(dA), Lp, b * h * w, L, Lp, stream())
+        return dx, dA
+
+
 # --------------------------------------------------------------------------------------------------
 # image packing (network input boundary)
 # --------------------------------------------------------------------------------------------------
