@@ -96,28 +96,47 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const float* __res
         ldg8f(scale + c8 * 8, sc);
         ldg8f(shift + c8 * 8, sh);
     }
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long p = i / C8;
-        float v[8];
-        Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, v);
-        if (!hoist) {
-            ldg8f(scale + c8 * 8, sc);
-            ldg8f(shift + c8 * 8, sh);
+    // two independent vectors per trip (loads issued back to back before the math) keep more bytes in flight
+    constexpr int kU = 2;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x; i0 < total; i0 += kU * stride) {
+        uint4 xq[kU], rq[kU];
+        long long off_y[kU];
+        int c8s[kU];
+        bool ok[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = i0 + u * stride;
+            ok[u] = i < total;
+            const long long ii = ok[u] ? i : i0;
+            c8s[u] = (int)(ii % C8);
+            const long long p = ii / C8;
+            xq[u] = *reinterpret_cast<const uint4*>(x + p * xcs + c8s[u] * 8);
+            if (kRes) rq[u] = *reinterpret_cast<const uint4*>(res + p * rcs + c8s[u] * 8);
+            off_y[u] = p * ycs + c8s[u] * 8;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
-        if (kRes) {
-            float r[8];
-            Vec8<__nv_bfloat16>::load(res + p * rcs + c8 * 8, r);
+        for (int u = 0; u < kU; ++u) {
+            float v[8];
+            unpack8(xq[u], v);
+            if (!hoist) {
+                ldg8f(scale + c8s[u] * 8, sc);
+                ldg8f(shift + c8s[u] * 8, sh);
+            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += r[k];
-        }
-        if (kRelu) {
+            for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+            if (kRes) {
+                float r[8];
+                unpack8(rq[u], r);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+                for (int k = 0; k < 8; ++k) v[k] += r[k];
+            }
+            if (kRelu) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+            }
+            if (ok[u]) Vec8<__nv_bfloat16>::store(y + off_y[u], v);
         }
-        Vec8<__nv_bfloat16>::store(y + p * ycs + c8 * 8, v);
     }
 }
 
@@ -145,7 +164,39 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_
         for (int k = 0; k < 8; ++k) { a0[k] = 0.f; a1[k] = 0.f; sc[k] = 0.f; sh[k] = 0.f; }
         if (cg < C8 && lane < lanes) {
             if (kRelu == 2) { ldg8f(scale + cg * 8, sc); ldg8f(shift + cg * 8, sh); }
-            for (long long pp = p0 + lane; pp < p1; pp += lanes) {
+            // kU independent pixel rows per trip: all 2-3 x kU 16-byte loads are issued before the first use, so each
+            // thread keeps >= 128 B in flight (the pass is pure HBM streaming; one load pair per trip left the memory
+            // pipe at ~3.4 TB/s)
+            constexpr int kU = 4;
+            long long pp = p0 + lane;
+            for (; pp + (long long)(kU - 1) * lanes < p1; pp += (long long)kU * lanes) {
+                uint4 gq[kU], xq[kU], yq[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const long long q = pp + (long long)u * lanes;
+                    gq[u] = *reinterpret_cast<const uint4*>(dy + q * dycs + cg * 8);
+                    xq[u] = *reinterpret_cast<const uint4*>(x + q * xcs + cg * 8);
+                    if (kRelu == 1) yq[u] = *reinterpret_cast<const uint4*>(y + q * ycs + cg * 8);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    float gv[8], xv[8];
+                    unpack8(gq[u], gv);
+                    unpack8(xq[u], xv);
+                    if (kRelu == 1) {
+                        float yv[8];
+                        unpack8(yq[u], yv);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) gv[k] = yv[k] > 0.f ? gv[k] : 0.f;
+                    } else if (kRelu == 2) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) gv[k] = fmaf(xv[k], sc[k], sh[k]) > 0.f ? gv[k] : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { a0[k] += gv[k]; a1[k] = fmaf(gv[k], xv[k], a1[k]); }
+                }
+            }
+            for (; pp < p1; pp += lanes) {
                 float gv[8], xv[8];
                 Vec8<__nv_bfloat16>::load(dy + pp * dycs + cg * 8, gv);
                 Vec8<__nv_bfloat16>::load(x + pp * xcs + cg * 8, xv);
@@ -221,26 +272,46 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_b
 #pragma unroll
     for (int k = 0; k < 8; ++k) { sc[k] = 0.f; sh[k] = 0.f; }
     if (hoist) coeffs(threadIdx.x % C8, A, B, Cc, sc, sh);
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long p = i / C8;
-        if (!hoist) coeffs(c8, A, B, Cc, sc, sh);
-        float g[8], xv[8], o[8];
-        Vec8<__nv_bfloat16>::load(dy + p * dycs + c8 * 8, g);
-        Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, xv);
-        if (kRelu == 1) {
-            float yv[8];
-            Vec8<__nv_bfloat16>::load(y + p * ycs + c8 * 8, yv);
+    constexpr int kU = 2;   // two independent vectors per trip: 4-6 loads in flight per thread before the math
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x; i0 < total; i0 += kU * stride) {
+        uint4 gq[kU], xq[kU], yq[kU];
+        long long pix[kU];
+        int c8s[kU];
+        bool ok[kU];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
-        } else if (kRelu == 2) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = fmaf(xv[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+        for (int u = 0; u < kU; ++u) {
+            const long long i = i0 + u * stride;
+            ok[u] = i < total;
+            const long long ii = ok[u] ? i : i0;
+            c8s[u] = (int)(ii % C8);
+            pix[u] = ii / C8;
+            gq[u] = *reinterpret_cast<const uint4*>(dy + pix[u] * dycs + c8s[u] * 8);
+            xq[u] = *reinterpret_cast<const uint4*>(x + pix[u] * xcs + c8s[u] * 8);
+            if (kRelu == 1) yq[u] = *reinterpret_cast<const uint4*>(y + pix[u] * ycs + c8s[u] * 8);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], g[k], fmaf(B[k], xv[k], Cc[k]));
-        Vec8<__nv_bfloat16>::store(dx + p * dxcs + c8 * 8, o);
-        if (kDres) Vec8<__nv_bfloat16>::store(dres + p * drcs + c8 * 8, g);
+        for (int u = 0; u < kU; ++u) {
+            if (!hoist) coeffs(c8s[u], A, B, Cc, sc, sh);
+            float g[8], xv[8], o[8];
+            unpack8(gq[u], g);
+            unpack8(xq[u], xv);
+            if (kRelu == 1) {
+                float yv[8];
+                unpack8(yq[u], yv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = yv[k] > 0.f ? g[k] : 0.f;
+            } else if (kRelu == 2) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = fmaf(xv[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], g[k], fmaf(B[k], xv[k], Cc[k]));
+            if (ok[u]) {
+                Vec8<__nv_bfloat16>::store(dx + pix[u] * dxcs + c8s[u] * 8, o);
+                if (kDres) Vec8<__nv_bfloat16>::store(dres + pix[u] * drcs + c8s[u] * 8, g);
+            }
+        }
     }
 }
 

@@ -488,12 +488,14 @@ int launch_v2(const V2Params& prm, int grid_x, int n_tiles, size_t smem, cudaStr
 
 }  // namespace
 
+extern int g_tsb_ohem_hoist;
 extern "C" int tsb_debug_set(int key, int value) {
     if (key == 1) g_use_base_offset = value;
     else if (key == 2) g_allow_rows = value;
     else if (key == 3) g_allow_resident = value;
     else if (key == 4) convv2::g_enabled = value;
     else if (key == 5) { g_wgrad_waves = value; convv2::g_wgrad_waves_x = value; }
+    else if (key == 6) g_tsb_ohem_hoist = value;
     else return TSB_ERR_ARG;
     return TSB_OK;
 }

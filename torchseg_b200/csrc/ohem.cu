@@ -37,10 +37,13 @@ __device__ __forceinline__ Lerp make_lerp(float scale, int dst, int in_size) {
     r.l0 = __fsub_rn(1.0f, r.l1);
     return r;
 }
-__device__ __forceinline__ float lerp4(const Lerp& ly, const Lerp& lx, float a, float b, float c, float d) {
-    // no FMA contraction: identical to the oracle's separate multiply/add sequence
-    float t0 = __fadd_rn(__fmul_rn(lx.l0, a), __fmul_rn(lx.l1, b));
-    float t1 = __fadd_rn(__fmul_rn(lx.l0, c), __fmul_rn(lx.l1, d));
+// 4-tap bilinear blend in the oracle's operation order (no FMA contraction: separate multiply / add roundings),
+// split at its own intermediate values: t = horizontal blend of one source row (depends on the column only, so a band
+// kernel forms it ONCE per thread), v = vertical blend per hi-res row.
+__device__ __forceinline__ float lerp_h(const Lerp& lx, float a, float b) {
+    return __fadd_rn(__fmul_rn(lx.l0, a), __fmul_rn(lx.l1, b));
+}
+__device__ __forceinline__ float lerp_v(const Lerp& ly, float t0, float t1) {
     return __fadd_rn(__fmul_rn(ly.l0, t0), __fmul_rn(ly.l1, t1));
 }
 __host__ __device__ __forceinline__ float area_scale(int in_size, int out_size) {
@@ -178,8 +181,8 @@ __device__ __forceinline__ BandGeom band_geom(float ry, float rx, int ci, int x0
     return g;
 }
 
-template <int CMAX>
-__global__ void __launch_bounds__(kThreads)
+template <int CMAX, bool kHoist>
+__global__ void __launch_bounds__(kThreads, kHoist ? 2 : 1)
 ohem_ptarget_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64_t* __restrict__ labels, int N,
                        int C, int H, int W, int ignore_label, float thresh, float* __restrict__ p,
                        float* __restrict__ nll, uint32_t* state, int maxcols) {
@@ -202,6 +205,15 @@ ohem_ptarget_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const
     const bool xin = x < x1;
     const Lerp lx = make_lerp(rx, xin ? x : x0, w);
     const int j0 = lx.i0 - g.jbase, j1 = lx.i1 - g.jbase;
+    float t0[CMAX], t1[CMAX];   // horizontally blended source rows of this thread's column (row-invariant)
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        t0[c] = 0.f; t1[c] = 0.f;
+        if (kHoist && c < C) {
+            t0[c] = lerp_h(lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c]);
+            t1[c] = lerp_h(lx, s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
+        }
+    }
     for (int y = g.y_lo; y <= g.y_hi; ++y) {
         const Lerp ly = make_lerp(ry, y, h);
         if (ly.i0 != ci || !xin) continue;  // uniform in y across the CTA
@@ -212,7 +224,10 @@ ohem_ptarget_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const
         float v[CMAX];
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-            if (c < C) v[c] = lerp4(ly, lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c], s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
+            if (c < C)
+                v[c] = kHoist ? lerp_v(ly, t0[c], t1[c])
+                              : lerp_v(ly, lerp_h(lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c]),
+                                       lerp_h(lx, s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]));
         float p_t, nl;
         softmax_target<CMAX>(v, C, t, p_t, nl);
         pt_emit(i, valid, p_t, nl, thresh, p, nll, acc);
@@ -429,8 +444,8 @@ ohem_grad_kernel(const T* __restrict__ logits, long long sn, long long sc, long 
 //            column j and accumulates top += l0(y)*s, bot += l1(y)*s in registers.
 // After the band: red.global.add of top → row i, bot → row i1.  No shuffles, no per-pixel atomics.
 // ---------------------------------------------------------------------------------------------
-template <int CMAX>
-__global__ void __launch_bounds__(kThreads)
+template <int CMAX, bool kHoist>
+__global__ void __launch_bounds__(kThreads, kHoist ? 2 : 1)
 ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64_t* __restrict__ labels,
                     const float* __restrict__ p, int N, int C, int H, int W, int ignore_label,
                     const float* __restrict__ cw, const uint32_t* __restrict__ state,
@@ -470,9 +485,15 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
         for (int jj = jprev + 1; jj <= j0; ++jj) s_seg[jj] = (short)threadIdx.x;
     }
     // ---- phase 1: per-thread accumulation over the rows of the band (registers only)
-    float G0[CMAX], G1[CMAX];
+    float G0[CMAX], G1[CMAX], t0[CMAX], t1[CMAX];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) { G0[c] = 0.f; G1[c] = 0.f; }
+    for (int c = 0; c < CMAX; ++c) {
+        G0[c] = 0.f; G1[c] = 0.f; t0[c] = 0.f; t1[c] = 0.f;
+        if (kHoist && c < C && xin) {   // horizontally blended source rows: row-invariant, formed once per band
+            t0[c] = lerp_h(lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c]);
+            t1[c] = lerp_h(lx, s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
+        }
+    }
     for (int y = g.y_lo; y <= g.y_hi; ++y) {
         const Lerp ly = make_lerp(ry, y, h);
         if (ly.i0 != ci || !xin) continue;
@@ -487,7 +508,9 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
             if (c < C) {
-                v[c] = lerp4(ly, lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c], s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
+                v[c] = kHoist ? lerp_v(ly, t0[c], t1[c])
+                              : lerp_v(ly, lerp_h(lx, s_lo0[j0 * CMAX + c], s_lo0[j1 * CMAX + c]),
+                                       lerp_h(lx, s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]));
                 m = fmaxf(m, v[c]);
             }
         float ssum = 0.f;
@@ -541,6 +564,9 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
 
 }  // namespace
 
+// A/B switch (tsb_debug_set key 6): 1 = band kernels keep the horizontally blended source rows in registers
+int g_tsb_ohem_hoist = 1;
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -591,10 +617,10 @@ extern "C" int tsb_ohem_ptarget_up(const float* logits_lo, int cs, int h, int w,
     const size_t smem = sizeof(float) * 2 * (size_t)maxcols * cmax;
     TSB_REQUIRE(smem <= 28 * 1024, "tsb_ohem_ptarget_up: up-scale factor W/w too small for the band kernel");
     dim3 grid((W + kStrip - 1) / kStrip, h, N);
-    if (C <= 20)
-        ohem_ptarget_up_kernel<20><<<grid, kThreads, smem, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state, maxcols);
-    else
-        ohem_ptarget_up_kernel<32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state, maxcols);
+#define L(CM, HO) ohem_ptarget_up_kernel<CM, HO><<<grid, kThreads, smem, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state, maxcols)
+    if (C <= 20) { if (g_tsb_ohem_hoist) L(20, true); else L(20, false); }
+    else { if (g_tsb_ohem_hoist) L(32, true); else L(32, false); }
+#undef L
     TSB_CUDA_CHECK_LAUNCH("ohem_ptarget_up");
     return TSB_OK;
 }
@@ -662,15 +688,18 @@ extern "C" int tsb_ohem_grad_up(const float* logits_lo, int cs, int h, int w, co
     TSB_REQUIRE(smem <= 96 * 1024, "tsb_ohem_grad_up: shared memory budget exceeded");
     dim3 grid((W + kStrip - 1) / kStrip, h, N);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C <= 20) {
-        static bool attr = false;
-        if (!attr) { TSB_CUDA_CALL(cudaFuncSetAttribute(ohem_grad_up_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-        ohem_grad_up_kernel<20><<<grid, kThreads, smem, st>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols);
-    } else {
-        static bool attr = false;
-        if (!attr) { TSB_CUDA_CALL(cudaFuncSetAttribute(ohem_grad_up_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-        ohem_grad_up_kernel<32><<<grid, kThreads, smem, st>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols);
-    }
+#define L(CM, HO)                                                                                                       \
+    do {                                                                                                                \
+        static bool attr = false;                                                                                       \
+        if (!attr) {                                                                                                    \
+            TSB_CUDA_CALL(cudaFuncSetAttribute(ohem_grad_up_kernel<CM, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+            attr = true;                                                                                                \
+        }                                                                                                               \
+        ohem_grad_up_kernel<CM, HO><<<grid, kThreads, smem, st>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols); \
+    } while (0)
+    if (C <= 20) { if (g_tsb_ohem_hoist) L(20, true); else L(20, false); }
+    else { if (g_tsb_ohem_hoist) L(32, true); else L(32, false); }
+#undef L
     TSB_CUDA_CHECK_LAUNCH("ohem_grad_up");
     return TSB_OK;
 }

@@ -154,7 +154,11 @@ __device__ __forceinline__ float tsb_exp_det(float x) {
     const float LN2_HI = 0.693145751953125f;          // 0x3f317200
     const float LN2_LO = 1.428606765330187e-06f;      // ln2 - LN2_HI
     float t = __fmul_rn(x, LOG2E);
-    float n = rintf(t);
+    // n = rintf(t) (round-to-nearest-even) via the 1.5*2^23 trick: exact for |t| < 2^22 (here t in [-151, 0]) and it
+    // yields the integer in the low mantissa bits, so neither FRND nor F2I (quarter-rate conversion pipe) is issued
+    const float MAGIC = 12582912.0f;   // 0x4B400000
+    float z = __fadd_rn(t, MAGIC);
+    float n = __fsub_rn(z, MAGIC);
     float r = fmaf(n, -LN2_HI, x);
     r = fmaf(n, -LN2_LO, r);
     // degree-6 polynomial for e^r on [-ln2/2, ln2/2]
@@ -165,7 +169,7 @@ __device__ __forceinline__ float tsb_exp_det(float x) {
     p = fmaf(p, r, 0.5f);
     p = fmaf(p, r, 1.0f);
     p = fmaf(p, r, 1.0f);
-    int ni = (int)n;  // in [-151, 0]
+    int ni = __float_as_int(z) - 0x4B400000;  // == (int)n, in [-151, 0]
     // scale by 2^ni in two exact steps so subnormal results round once, like the oracle
     int n1 = ni / 2, n2 = ni - n1;
     float s1 = __int_as_float((n1 + 127) << 23);
