@@ -267,6 +267,16 @@ int tsb_bias_grad(const void* dy, int dycs, long long npix, int K, float* db, ts
 int tsb_sgd_flat(float* param, const float* grad, float* mom_buf, long long n, const long long* seg_end,
                  const float* seg_lr, const float* seg_wd, int nseg, float momentum, float gscale, int first_step,
                  tsb_stream_t stream);
+/* same update, and additionally param_bf16[i] = bf16(param[i]) for the whole flat buffer: conv weights are stored
+ * KRSC, so the bf16 copy IS the fprop/wgrad weight operand of every layer (no per-layer pack launches next step) */
+int tsb_sgd_flat_pack(float* param, const float* grad, float* mom_buf, long long n, const long long* seg_end,
+                      const float* seg_lr, const float* seg_wd, int nseg, float momentum, float gscale, int first_step,
+                      void* param_bf16, tsb_stream_t stream);
+/* all dgrad weight operands in one launch: for tensor t (descriptor {int64 off; int32 K, RS, C, tiles_k, tiles_c, pad}
+ * = 32 bytes, tiles_* = ceil(./32)), wt_flat[off + ((c*RS + RS-1-rs)*K + k)] = wb_flat[off + ((k*RS + rs)*C + c)].
+ * block_start[t] = first block of tensor t (blocks per tensor = RS * tiles_k * tiles_c), nblocks = their sum. */
+int tsb_pack_wt_multi(const void* wb_flat_bf16, void* wt_flat_bf16, const void* desc, const int* block_start,
+                      int ntensors, int nblocks, tsb_stream_t stream);
 
 /* ================================================================================================
  * Sigmoid focal loss (DFN border branch) — SigmoidFocalLoss.forward loss_opr.py:23-45, reproduced

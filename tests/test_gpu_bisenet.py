@@ -327,3 +327,37 @@ def test_pspnet_r101_step_matches_oracle(cuda):
             assert 0.8 < ratio < 1.25, (n, ratio)
             checked += 1
     assert checked >= 100
+
+
+def test_flat_bf16_mirror_matches_per_tensor_pack(cuda):
+    """after an optimiser step the bf16 mirror written by tsb_sgd_flat_pack / tsb_pack_wt_multi must be bit-identical to
+    the per-tensor tsb_pack_weight operands (fprop/wgrad KRSC copy and the flipped-transposed dgrad copy)"""
+    from torchseg_b200 import optim, ops
+    from torchseg_b200.utils.init_func import group_weight
+    model, sd, x, y, _ = _build(cuda, N=2, HW=64, seed=5)
+    groups = group_weight([], model, BN, 1e-2)
+    opt = optim.SGD(groups, lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    opt.zero_grad()
+    loss = model(x.to(cuda), y.to(cuda))
+    loss.backward()
+    opt.step()
+    checked = 0
+    for n, p in model.named_parameters():
+        if p.dim() != 4 or p.shape[1] % 8 != 0 or p.shape[0] % 8 != 0:
+            continue
+        fp, idx = p._tsb_pack
+        hit = fp.lookup(p, idx, True)
+        assert hit is not None, n
+        wb, wt = hit
+        K, C, R, S = p.shape
+        ref_b = p.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
+        ref_t = ref_b.flip(1, 2).permute(3, 1, 2, 0).contiguous()
+        assert torch.equal(wb, ref_b), n
+        assert torch.equal(wt, ref_t), n
+        checked += 1
+    assert checked >= 30
+    # an in-place edit of a weight invalidates its mirror entry (falls back to the per-tensor pack)
+    p = model.ffm.conv_1x1.conv.weight
+    with torch.no_grad():
+        p.mul_(0.5)
+    assert p._tsb_pack[0].lookup(p, p._tsb_pack[1], False) is None

@@ -68,6 +68,8 @@ _SIGS = {
     "tsb_conv_stem_wgrad": [P, I, I, I, P, I, I, P, P],
     "tsb_bias_grad": [P, I, L, I, P, P],
     "tsb_sgd_flat": [P, P, P, L, P, P, P, I, F, F, I, P],
+    "tsb_sgd_flat_pack": [P, P, P, L, P, P, P, I, F, F, I, P, P],
+    "tsb_pack_wt_multi": [P, P, P, P, I, I, P],
     "tsb_sigmoid_focal_fwd_bwd": [P, I, P, L, I, F, F, P, P, P],
 }
 EXPORTS = sorted(list(_SIGS) + ["tsb_last_error", "tsb_version", "tsb_launch_count"])
@@ -92,6 +94,10 @@ def lib():
         h.tsb_last_error.argtypes = []
         h.tsb_version.restype = c_int
         h.tsb_launch_count.restype = c_longlong
+        # developer A/B switches (include/tsb.h tsb_debug_set): TSB_DEBUG_SET="6=0,5=2"
+        for kv in filter(None, os.environ.get("TSB_DEBUG_SET", "").split(",")):
+            k, v = kv.split("=")
+            h.tsb_debug_set(int(k), int(v))
         _lib = h
     return _lib
 

@@ -1,5 +1,6 @@
 """ResNet v1 / v1c backbone with the reference's constructor and attribute names
 (/root/reference/furnace/base_model/resnet.py); forward runs the fused libtsb path."""
+import torch
 import torch.nn as nn
 
 from .. import ops
@@ -32,12 +33,14 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         x = _as_act(x)
-        out = conv_bn_act(x, self.conv1, self.bn1, True)
-        residual = x
+        # x is consumed twice inside the block (conv1 + shortcut): their input gradients share one buffer
+        share = ops.GradShare(2) if (x.requires_grad and torch.is_grad_enabled()) else None
+        out = conv_bn_act(x, self.conv1, self.bn1, True, in_share=share)
         if self.downsample is not None:
-            residual = conv_bn_act(x, self.downsample[0], self.downsample[1], False)
+            residual = conv_bn_act(x, self.downsample[0], self.downsample[1], False, in_share=share)
+            return conv_bn_act(out, self.conv2, self.bn2, True, residual=residual)
         # conv2 → bn2 → (+residual) → relu in one fused group (resnet.py:42-51)
-        return conv_bn_act(out, self.conv2, self.bn2, True, residual=residual)
+        return conv_bn_act(out, self.conv2, self.bn2, True, residual=x, res_share=share)
 
 
 class Bottleneck(nn.Module):
@@ -61,12 +64,13 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         x = _as_act(x)
-        out = conv_bn_act(x, self.conv1, self.bn1, True)
+        share = ops.GradShare(2) if (x.requires_grad and torch.is_grad_enabled()) else None   # see BasicBlock.forward
+        out = conv_bn_act(x, self.conv1, self.bn1, True, in_share=share)
         out = conv_bn_act(out, self.conv2, self.bn2, True)
-        residual = x
         if self.downsample is not None:
-            residual = conv_bn_act(x, self.downsample[0], self.downsample[1], False)
-        return conv_bn_act(out, self.conv3, self.bn3, True, residual=residual)
+            residual = conv_bn_act(x, self.downsample[0], self.downsample[1], False, in_share=share)
+            return conv_bn_act(out, self.conv3, self.bn3, True, residual=residual)
+        return conv_bn_act(out, self.conv3, self.bn3, True, residual=x, res_share=share)
 
 
 class ResNet(nn.Module):

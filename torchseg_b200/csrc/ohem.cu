@@ -214,11 +214,15 @@ ohem_ptarget_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const
             t1[c] = lerp_h(lx, s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
         }
     }
+    // software pipeline: the label of row y+1 is requested before row y is evaluated (the row body is ~900 issue
+    // slots, enough to cover the global-load latency at 8-16 resident warps)
+    long long lab_next = xin ? labels[((long long)n * H + g.y_lo) * W + x] : 0;
     for (int y = g.y_lo; y <= g.y_hi; ++y) {
+        const long long lab = lab_next;
+        if (xin && y < g.y_hi) lab_next = labels[((long long)n * H + y + 1) * W + x];
         const Lerp ly = make_lerp(ry, y, h);
         if (ly.i0 != ci || !xin) continue;  // uniform in y across the CTA
         const long long i = ((long long)n * H + y) * W + x;
-        long long lab = labels[i];
         bool valid = lab != (long long)ignore_label;
         int t = valid ? (int)lab : 0;
         float v[CMAX];
@@ -494,12 +498,25 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
             t1[c] = lerp_h(lx, s_lo1[j0 * CMAX + c], s_lo1[j1 * CMAX + c]);
         }
     }
+    // software pipeline: label and p of row y+1 are requested before row y is evaluated
+    long long lab_next = 0;
+    float p_next = 0.f;
+    if (xin) {
+        const long long q0 = ((long long)n * H + g.y_lo) * W + x;
+        lab_next = labels[q0];
+        p_next = active ? p[q0] : 0.f;
+    }
     for (int y = g.y_lo; y <= g.y_hi; ++y) {
+        const long long lab = lab_next;
+        const float pv = p_next;
+        if (xin && y < g.y_hi) {
+            const long long q1 = ((long long)n * H + y + 1) * W + x;
+            lab_next = labels[q1];
+            p_next = active ? p[q1] : 0.f;
+        }
         const Lerp ly = make_lerp(ry, y, h);
         if (ly.i0 != ci || !xin) continue;
-        const long long pi = ((long long)n * H + y) * W + x;
-        const long long lab = labels[pi];
-        const bool kept = (lab != (long long)ignore_label) && (!active || p[pi] <= Tth);
+        const bool kept = (lab != (long long)ignore_label) && (!active || pv <= Tth);
         if (!kept) continue;
         const int t = (int)lab;
         const float wt = (cw ? __ldg(cw + t) : 1.f) * scale;
@@ -564,7 +581,9 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
 
 }  // namespace
 
-// A/B switch (tsb_debug_set key 6): 1 = band kernels keep the horizontally blended source rows in registers
+// A/B switch (tsb_debug_set key 6): band kernels keep the horizontally blended source rows in registers; bit 0 =
+// gradient kernel (measured 2.16 -> 1.85 ms/step), bit 1 = p_target kernel (measured slower: 111 registers halve the
+// occupancy of an issue-bound kernel, 1.72 -> 1.85 ms) — default 1.
 int g_tsb_ohem_hoist = 1;
 
 // =============================================================================================
@@ -618,8 +637,8 @@ extern "C" int tsb_ohem_ptarget_up(const float* logits_lo, int cs, int h, int w,
     TSB_REQUIRE(smem <= 28 * 1024, "tsb_ohem_ptarget_up: up-scale factor W/w too small for the band kernel");
     dim3 grid((W + kStrip - 1) / kStrip, h, N);
 #define L(CM, HO) ohem_ptarget_up_kernel<CM, HO><<<grid, kThreads, smem, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state, maxcols)
-    if (C <= 20) { if (g_tsb_ohem_hoist) L(20, true); else L(20, false); }
-    else { if (g_tsb_ohem_hoist) L(32, true); else L(32, false); }
+    if (C <= 20) { if (g_tsb_ohem_hoist & 2) L(20, true); else L(20, false); }
+    else { if (g_tsb_ohem_hoist & 2) L(32, true); else L(32, false); }
 #undef L
     TSB_CUDA_CHECK_LAUNCH("ohem_ptarget_up");
     return TSB_OK;
@@ -697,8 +716,8 @@ extern "C" int tsb_ohem_grad_up(const float* logits_lo, int cs, int h, int w, co
         }                                                                                                               \
         ohem_grad_up_kernel<CM, HO><<<grid, kThreads, smem, st>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols); \
     } while (0)
-    if (C <= 20) { if (g_tsb_ohem_hoist) L(20, true); else L(20, false); }
-    else { if (g_tsb_ohem_hoist) L(32, true); else L(32, false); }
+    if (C <= 20) { if (g_tsb_ohem_hoist & 1) L(20, true); else L(20, false); }
+    else { if (g_tsb_ohem_hoist & 1) L(32, true); else L(32, false); }
 #undef L
     TSB_CUDA_CHECK_LAUNCH("ohem_grad_up");
     return TSB_OK;

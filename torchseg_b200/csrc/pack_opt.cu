@@ -172,7 +172,8 @@ bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, long long npix,
 __global__ void __launch_bounds__(kThreads)
 sgd_flat_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ mom, long long n,
                 const long long* __restrict__ seg_end, const float* __restrict__ seg_lr,
-                const float* __restrict__ seg_wd, int nseg, float momentum, float gscale, int first_step) {
+                const float* __restrict__ seg_wd, int nseg, float momentum, float gscale, int first_step,
+                __nv_bfloat16* __restrict__ param_bf16) {
     for (long long i4 = ((long long)blockIdx.x * kThreads + threadIdx.x) * 4; i4 < n; i4 += (long long)gridDim.x * kThreads * 4) {
         // all four elements may straddle a segment boundary → per-element lookup only when needed
         int lo = 0, hi = nseg - 1;
@@ -192,6 +193,8 @@ sgd_flat_kernel(float* __restrict__ param, const float* __restrict__ grad, float
             p.x -= lr * b.x; p.y -= lr * b.y; p.z -= lr * b.z; p.w -= lr * b.w;
             *reinterpret_cast<float4*>(mom + i4) = b;
             *reinterpret_cast<float4*>(param + i4) = p;
+            if (param_bf16)   // bf16 KRSC operand copy of the updated weights: the next step's convs read this directly
+                *reinterpret_cast<uint2*>(param_bf16 + i4) = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
         } else {
             for (long long i = i4; i < i4 + 4 && i < n; ++i) {
                 while (seg < nseg - 1 && seg_end[seg] <= i) ++seg;
@@ -200,8 +203,44 @@ sgd_flat_kernel(float* __restrict__ param, const float* __restrict__ grad, float
                 float b = first_step ? g : fmaf(momentum, mom[i], g);
                 mom[i] = b;
                 param[i] -= lr * b;
+                if (param_bf16) param_bf16[i] = __float2bfloat16_rn(param[i]);
             }
         }
+    }
+}
+
+// all dgrad weight operands in ONE launch: for every listed conv weight, wt[c][R-1-r][S-1-s][k] = wb[k][r][s][c]
+// (bf16 → bf16, both inside flat buffers at the same offset). 32x32 (k, c) tiles per filter tap through smem so
+// that both the read (along c) and the write (along k) are contiguous.
+struct WtDesc {
+    long long off;
+    int K, RS, C, tiles_k, tiles_c, pad;
+};
+__global__ void __launch_bounds__(256)
+pack_wt_multi_kernel(const __nv_bfloat16* __restrict__ wb, __nv_bfloat16* __restrict__ wt, const WtDesc* __restrict__ desc,
+                     const int* __restrict__ bstart, int nt) {
+    __shared__ unsigned short tile[32][33];
+    int lo = 0, hi = nt - 1;
+    const int b = blockIdx.x;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (bstart[mid] <= b) lo = mid; else hi = mid - 1; }
+    const WtDesc d = desc[lo];
+    int local = b - bstart[lo];
+    const int tc = local % d.tiles_c; local /= d.tiles_c;
+    const int tk = local % d.tiles_k;
+    const int rs = local / d.tiles_k;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(wb) + d.off;
+    unsigned short* dst = reinterpret_cast<unsigned short*>(wt) + d.off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = tk * 32 + ty + j * 8, c = tc * 32 + tx;
+        if (k < d.K && c < d.C) tile[ty + j * 8][tx] = src[((long long)k * d.RS + rs) * d.C + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = tc * 32 + ty + j * 8, k = tk * 32 + tx;
+        if (c < d.C && k < d.K) dst[((long long)c * d.RS + (d.RS - 1 - rs)) * d.K + k] = tile[tx][ty + j * 8];
     }
 }
 
@@ -342,8 +381,28 @@ extern "C" int tsb_sgd_flat(float* param, const float* grad, float* mom_buf, lon
     TSB_REQUIRE(param && grad && mom_buf && seg_end && seg_lr && seg_wd && n > 0 && nseg > 0, "tsb_sgd_flat: bad args");
     TSB_REQUIRE(tsb_aligned16(param) && tsb_aligned16(grad) && tsb_aligned16(mom_buf), "tsb_sgd_flat: buffers must be 16B aligned");
     int grid = tsb_grid_for((n + 3) / 4, kThreads, 8);
-    sgd_flat_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(param, grad, mom_buf, n, seg_end, seg_lr, seg_wd, nseg, momentum, gscale, first_step);
+    sgd_flat_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(param, grad, mom_buf, n, seg_end, seg_lr, seg_wd, nseg, momentum, gscale, first_step, nullptr);
     TSB_CUDA_CHECK_LAUNCH("sgd_flat");
+    return TSB_OK;
+}
+
+extern "C" int tsb_sgd_flat_pack(float* param, const float* grad, float* mom_buf, long long n, const long long* seg_end,
+                                 const float* seg_lr, const float* seg_wd, int nseg, float momentum, float gscale,
+                                 int first_step, void* param_bf16, tsb_stream_t stream) {
+    TSB_REQUIRE(param && grad && mom_buf && seg_end && seg_lr && seg_wd && param_bf16 && n > 0 && nseg > 0, "tsb_sgd_flat_pack: bad args");
+    TSB_REQUIRE(tsb_aligned16(param) && tsb_aligned16(grad) && tsb_aligned16(mom_buf) && tsb_aligned16(param_bf16),
+                "tsb_sgd_flat_pack: buffers must be 16B aligned");
+    int grid = tsb_grid_for((n + 3) / 4, kThreads, 8);
+    sgd_flat_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(param, grad, mom_buf, n, seg_end, seg_lr, seg_wd, nseg, momentum, gscale, first_step, (__nv_bfloat16*)param_bf16);
+    TSB_CUDA_CHECK_LAUNCH("sgd_flat_pack");
+    return TSB_OK;
+}
+
+extern "C" int tsb_pack_wt_multi(const void* wb_flat, void* wt_flat, const void* desc, const int* block_start, int ntensors,
+                                 int nblocks, tsb_stream_t stream) {
+    TSB_REQUIRE(wb_flat && wt_flat && desc && block_start && ntensors > 0 && nblocks > 0, "tsb_pack_wt_multi: bad args");
+    pack_wt_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)wb_flat, (__nv_bfloat16*)wt_flat, (const WtDesc*)desc, block_start, ntensors);
+    TSB_CUDA_CHECK_LAUNCH("pack_wt_multi");
     return TSB_OK;
 }
 

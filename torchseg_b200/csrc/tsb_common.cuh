@@ -146,16 +146,16 @@ template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bf
 // Deterministic expf shared bit-for-bit with oracle/tsb_oracle.c (tsb_exp_det there):
 // every operation is an explicit IEEE fp32 op (fmaf / mul / add), no fast-math, no contraction
 // ambiguity, so the CPU oracle and the GPU produce identical p_target bits (OHEM index parity).
-// Valid for x <= 0 (softmax arguments after max subtraction); returns 0 below -104.
+// Valid for x <= 0 (softmax arguments after max subtraction); returns 0 below -86.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tsb_exp_det(float x) {
-    if (x < -104.0f) return 0.0f;
+    if (x < -86.0f) return 0.0f;   // < 4.5e-38: cannot change a sum containing exp(0) = 1; keeps all results normal
     const float LOG2E = 1.4426950408889634f;
     const float LN2_HI = 0.693145751953125f;          // 0x3f317200
     const float LN2_LO = 1.428606765330187e-06f;      // ln2 - LN2_HI
     float t = __fmul_rn(x, LOG2E);
-    // n = rintf(t) (round-to-nearest-even) via the 1.5*2^23 trick: exact for |t| < 2^22 (here t in [-151, 0]) and it
-    // yields the integer in the low mantissa bits, so neither FRND nor F2I (quarter-rate conversion pipe) is issued
+    // n = rintf(t) (round-to-nearest-even) via the 1.5*2^23 trick: exact for |t| < 2^22 (here t in [-124.1, 0]) and it
+    // leaves the integer in the low mantissa bits, so neither FRND nor F2I (quarter-rate conversion pipe) is issued
     const float MAGIC = 12582912.0f;   // 0x4B400000
     float z = __fadd_rn(t, MAGIC);
     float n = __fsub_rn(z, MAGIC);
@@ -169,12 +169,9 @@ __device__ __forceinline__ float tsb_exp_det(float x) {
     p = fmaf(p, r, 0.5f);
     p = fmaf(p, r, 1.0f);
     p = fmaf(p, r, 1.0f);
-    int ni = __float_as_int(z) - 0x4B400000;  // == (int)n, in [-151, 0]
-    // scale by 2^ni in two exact steps so subnormal results round once, like the oracle
-    int n1 = ni / 2, n2 = ni - n1;
-    float s1 = __int_as_float((n1 + 127) << 23);
-    float s2 = __int_as_float((n2 + 127) << 23);
-    return __fmul_rn(__fmul_rn(p, s1), s2);
+    // p * 2^n on the exponent field (exact: the result is normal). (bits(z) << 23) == (n << 23) mod 2^32 because the
+    // magic constant's own bits are shifted out.
+    return __int_as_float(__float_as_int(p) + (int)((unsigned)__float_as_int(z) << 23));
 }
 
 #endif  // __CUDACC__

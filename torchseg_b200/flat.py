@@ -6,13 +6,14 @@ def flatten(params, attr, like_data=True):
     """Make every tensor `getattr(p, attr)` (attr in {'data','grad'}) a view into ONE contiguous fp32 buffer,
     preserving each parameter's strides (KRSC conv weights stay KRSC). Returns (flat, spans)."""
     dev = params[0].device
-    # every span starts on a 16-byte boundary (float4 / red.v4 paths); the padding stays zero forever
-    n = sum((p.numel() + 3) // 4 * 4 for p in params)
+    # every span starts on a 32-byte boundary: float4 / red.v4 paths need 16 B, and the bf16 mirror of the parameter
+    # buffer (optim.FlatPack) must keep every weight 16-byte aligned for the TMA descriptors; the padding stays zero
+    n = sum((p.numel() + 7) // 8 * 8 for p in params)
     flat = torch.zeros(n, dtype=torch.float32, device=dev)
     spans = []
     off = 0
     for p in params:
-        k = (p.numel() + 3) // 4 * 4
+        k = (p.numel() + 7) // 8 * 8
         view = torch.as_strided(flat, p.shape, p.stride(), off)
         if attr == "data":
             view.copy_(p.data)

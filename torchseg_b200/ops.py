@@ -92,6 +92,11 @@ class _PackCache:
         zero_arena.reset()
 
     def get(self, w, want_t, pad_k=None, stem=False):
+        fp = getattr(w, "_tsb_pack", None)
+        if fp is not None and not stem and pad_k is None:
+            hit = fp[0].lookup(w, fp[1], want_t)   # bf16 mirror of the flat parameter buffer (optim.FlatPack)
+            if hit is not None:
+                return hit
         key = (id(w), w.data_ptr(), bool(want_t), pad_k, stem, w._version)
         hit = self.cache.get(key)
         if hit is not None and hit[2]() is w:
@@ -271,6 +276,35 @@ def _new_wgrad(w):
 # --------------------------------------------------------------------------------------------------
 # Conv + (Sync)BatchNorm(train) + residual + ReLU  — ConvBnRelu / BasicBlock tail
 # --------------------------------------------------------------------------------------------------
+class GradShare(object):
+    """One gradient buffer for a tensor consumed `n` times inside a block (x → conv1, x → downsample, x → residual).
+
+    Each consumer's backward calls contribute(g): the first stores its gradient and returns None to autograd; later ones
+    have already ACCUMULATED into the stored buffer (conv_dgrad(out=stash, accumulate=True)) and the last returns it. The
+    sum therefore reaches autograd as a single tensor and the element-wise bf16 adds (one read-read-write pass over
+    the activation per fork) disappear. Consumers outside the block are untouched: autograd adds their gradient to the
+    returned tensor as usual."""
+
+    def __init__(self, n):
+        self.n = n
+        self.left = n
+        self.stash = None
+
+    def contribute(self, g, accumulated=False):
+        """g: this consumer's input gradient; accumulated=True means g IS the stash (the consumer's dgrad epilogue added
+        into it in place). Returns what the consumer hands to autograd: None until the last contributor."""
+        self.left -= 1
+        if self.stash is None:
+            self.stash = g
+        elif not accumulated:
+            self.stash = self.stash + g   # a contributor that cannot accumulate in place arrived late (not the case for
+            #                               the block orders used here: the shortcut's backward always runs first)
+        if self.left > 0:
+            return None
+        out, self.stash, self.left = self.stash, None, self.n
+        return out
+
+
 class ConvBNActFn(torch.autograd.Function):
     """y = act(BN_train(conv(x, w)) + residual).
 
@@ -282,7 +316,7 @@ class ConvBNActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, gamma, beta, residual, running_mean, running_var, stride, pad, dil, relu, eps, momentum,
-                training, stem):
+                training, stem, in_share=None, res_share=None):
         K = w.shape[0]
         R = w.shape[2]
         dev = x.device
@@ -321,6 +355,11 @@ class ConvBNActFn(torch.autograd.Function):
         ctx.save_for_backward(x, w, gamma, raw, y, aux)
         ctx.beta_ref = beta
         ctx.cfg = (stride, pad, dil, relu, stem, residual is not None, count, training)
+        # gradient sharing at a fork (GradShare): in_share — this conv's input x has other consumers in the same block;
+        # res_share — the residual IS that x. The contributors chain their input gradients through one buffer (dgrad
+        # epilogue accumulate) instead of handing autograd several tensors to add.
+        ctx.in_share = in_share
+        ctx.res_share = res_share if residual is not None else None
         return y
 
     @staticmethod
@@ -375,10 +414,19 @@ class ConvBNActFn(torch.autograd.Function):
             conv_wgrad(x, draw, K, R, stride, pad, dil, dw)
             if ctx.needs_input_grad[0]:
                 _, wt = pack_cache.get(w, True)
-                dx = conv_dgrad(draw, wt, x.shape, K, R, stride, pad, dil)
+                share = ctx.in_share
+                if share is not None and share.stash is not None:
+                    dx = conv_dgrad(draw, wt, x.shape, K, R, stride, pad, dil, out=share.stash, accumulate=True)
+                    dx = share.contribute(dx, accumulated=True)
+                else:
+                    dx = conv_dgrad(draw, wt, x.shape, K, R, stride, pad, dil)
+                    if share is not None:
+                        dx = share.contribute(dx)
+        if has_res and ctx.res_share is not None and ctx.needs_input_grad[4]:
+            dres = ctx.res_share.contribute(dres)
         if direct:
             _notify(w, gamma, beta)
-        return dx, dw_view, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
+        return dx, dw_view, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 class StemPairFn(torch.autograd.Function):

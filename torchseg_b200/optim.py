@@ -8,6 +8,67 @@ from ._lib import call, ptr, stream
 from .flat import flatten, ensure_flat_grads
 
 
+class FlatPack(object):
+    """bf16 mirror of the flat parameter buffer. `wb` (KRSC bf16, the fprop / wgrad weight operand of every conv) is
+    written by the SGD kernel itself; `wt` (flipped-transposed dgrad operand) of ALL conv weights is produced by one
+    tsb_pack_wt_multi launch the first time a dgrad asks for it after a step. ops.pack_cache consults this through
+    the `_tsb_pack = (FlatPack, index)` attribute set on every parameter."""
+
+    def __init__(self, params, spans, n, device):
+        self.params = params
+        self.spans = spans
+        self.wb_flat = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        self.wt_flat = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        self.fresh = False
+        self.wt_done = False
+        self.versions = [None] * len(params)
+        desc, bstart, nb = [], [], 0
+        self.wt_index = {}
+        import struct
+        for i, (p, (lo, hi)) in enumerate(zip(params, spans)):
+            if p.dim() == 4 and p.shape[1] % 8 == 0 and p.shape[0] % 8 == 0 and \
+                    p.permute(0, 2, 3, 1).is_contiguous():
+                K, C, R, S = p.shape
+                tk, tc = (K + 31) // 32, (C + 31) // 32
+                desc.append(struct.pack("<qiiiiii", lo, K, R * S, C, tk, tc, 0))
+                bstart.append(nb)
+                nb += R * S * tk * tc
+                self.wt_index[i] = True
+            p._tsb_pack = (self, i)
+        self.nblocks = nb
+        self.ntensors = len(desc)
+        if desc:
+            raw = torch.frombuffer(bytearray(b"".join(desc)), dtype=torch.uint8)
+            self.desc = raw.to(device)
+            self.bstart = torch.tensor(bstart, dtype=torch.int32, device=device)
+
+    def mark_fresh(self):
+        self.fresh = True
+        self.wt_done = False
+        self.versions = [p._version for p in self.params]
+
+    def lookup(self, w, idx, want_t):
+        """(wb, wt) views for parameter idx, or None when the mirror is stale for it"""
+        if not self.fresh or w._version != self.versions[idx] or w.dim() != 4:
+            return None
+        if not w.permute(0, 2, 3, 1).is_contiguous():
+            return None
+        lo = self.spans[idx][0]
+        K, C, R, S = w.shape
+        n = K * C * R * S
+        wb = self.wb_flat[lo:lo + n].view(K, R, S, C)
+        wt = None
+        if want_t:
+            if idx not in self.wt_index:
+                return None
+            if not self.wt_done:
+                call("tsb_pack_wt_multi", ptr(self.wb_flat), ptr(self.wt_flat), ptr(self.desc), ptr(self.bstart),
+                     self.ntensors, self.nblocks, stream())
+                self.wt_done = True
+            wt = self.wt_flat[lo:lo + n].view(C, R, S, K)
+        return wb, wt
+
+
 class SGD(object):
     def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
         groups = list(params)
@@ -27,6 +88,7 @@ class SGD(object):
         self.flat_param, self._spans = flatten(self._params, "data")
         self.flat_grad, _ = ensure_flat_grads(self._params)
         self.flat_mom = torch.zeros_like(self.flat_param)
+        self.pack = FlatPack(self._params, self._spans, self.flat_param.numel(), self.flat_param.device)
         ends, idx = [], 0
         for g in self.param_groups:
             idx += len(g["params"])
@@ -46,11 +108,12 @@ class SGD(object):
         dev = self.flat_param.device
         lr = torch.tensor([float(g["lr"]) for g in self.param_groups], dtype=torch.float32, device=dev)
         wd = torch.tensor([float(g["weight_decay"]) for g in self.param_groups], dtype=torch.float32, device=dev)
-        call("tsb_sgd_flat", ptr(self.flat_param), ptr(self.flat_grad), ptr(self.flat_mom), self.flat_param.numel(),
+        call("tsb_sgd_flat_pack", ptr(self.flat_param), ptr(self.flat_grad), ptr(self.flat_mom), self.flat_param.numel(),
              ptr(self._seg_end), ptr(lr), ptr(wd), len(self.param_groups), float(self.momentum), float(self.grad_scale),
-             1 if self._steps == 0 else 0, stream())
+             1 if self._steps == 0 else 0, ptr(self.pack.wb_flat), stream())
         self._steps += 1
-        ops.pack_cache.invalidate()  # bf16 weight packs are stale now
+        ops.pack_cache.invalidate()  # per-tensor bf16 packs are stale now
+        self.pack.mark_fresh()       # ... and the flat bf16 mirror written by the kernel above is current
 
     def state_dict(self):
         groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]

@@ -63,8 +63,9 @@ def _ragged(conv, x):
     return conv.in_channels != x.shape[1] or conv.in_channels % 64 != 0
 
 
-def conv_bn_act(x, conv, bn, relu, residual=None):
-    """fused conv → norm_layer(train/eval) → (+residual) → ReLU on the libtsb path"""
+def conv_bn_act(x, conv, bn, relu, residual=None, in_share=None, res_share=None):
+    """fused conv → norm_layer(train/eval) → (+residual) → ReLU on the libtsb path.
+    in_share / res_share: ops.GradShare of a block-level fork (see BasicBlock.forward)"""
     ks = conv.kernel_size[0]
     assert conv.kernel_size[0] == conv.kernel_size[1] and conv.groups == 1 and conv.bias is None
     stem = (conv.in_channels == 3 and conv.stride[0] == 2 and conv.dilation[0] == 1 and
@@ -87,9 +88,11 @@ def conv_bn_act(x, conv, bn, relu, residual=None):
         gamma, beta = _pad_vec(gamma, Kp, 1.0), _pad_vec(beta, Kp)
         with torch.no_grad():
             rm, rv = _pad_vec(rm, Kp), _pad_vec(rv, Kp, 1.0)
+    if padded or stem or not bn.training:
+        in_share = res_share = None
     y = ops.ConvBNActFn.apply(xin, w, gamma, beta, residual, rm, rv,
                               conv.stride[0], conv.padding[0], conv.dilation[0], bool(relu), float(bn.eps),
-                              float(momentum), bool(bn.training), stem)
+                              float(momentum), bool(bn.training), stem, in_share, res_share)
     if padded and bn.training and rm is not bn.running_mean:
         with torch.no_grad():
             bn.running_mean.copy_(rm[:K])
