@@ -4,8 +4,10 @@
 // statistics half of apex SyncBatchNorm (train.py:54-55).  All HBM-bound: 16-byte vector accesses,
 // per-channel reductions through shared memory + one fp32 atomic per (CTA, channel).
 #include "nhwc_vec.cuh"
+#include "sm100_ptx.cuh"
 
 namespace {
+using sm100::red_add_v4;
 constexpr int kThreads = 256;
 
 // Generic per-channel column reduction over [npix, C] with NACC accumulators per channel.
@@ -36,11 +38,15 @@ __device__ __forceinline__ void column_reduce(long long npix, int C8, float* con
         }
         __syncthreads();
         // thread (lane, g) finishes accumulator slots striped over lanes
+        // (16-byte vector reductions: a quarter of the atomic operations that all CTAs send to the same few L2 slices)
         if (cg < C8 && lane < lanes) {
-            for (int slot = lane; slot < NACC * 8; slot += lanes) {
-                float s = 0.f;
-                for (int l = 0; l < lanes; ++l) s += s_buf[(l * groups + g) * NACC * 8 + slot];
-                atomicAdd(outs[slot / 8] + cg * 8 + (slot % 8), s);
+            for (int quad = lane; quad < NACC * 2; quad += lanes) {
+                float s[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int l = 0; l < lanes; ++l) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s[k] += s_buf[(l * groups + g) * NACC * 8 + quad * 4 + k];
+                }
+                red_add_v4(outs[quad / 2] + cg * 8 + (quad % 2) * 4, s[0], s[1], s[2], s[3]);
             }
         }
         __syncthreads();
@@ -96,23 +102,30 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const float* __res
         ldg8f(scale + c8 * 8, sc);
         ldg8f(shift + c8 * 8, sh);
     }
-    // two independent vectors per trip (loads issued back to back before the math) keep more bytes in flight
+    // two independent vectors per trip (loads issued back to back before the math); (pixel, channel-group) indices
+    // come from a VecWalk — no 64-bit division in the loop
     constexpr int kU = 2;
     const long long stride = (long long)gridDim.x * kThreads;
-    for (long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x; i0 < total; i0 += kU * stride) {
+    const long long start = (long long)blockIdx.x * kThreads + threadIdx.x;
+    VecWalk wk(C8, start, stride);
+    for (long long i0 = start; i0 < total; i0 += kU * stride) {
         uint4 xq[kU], rq[kU];
         long long off_y[kU];
         int c8s[kU];
         bool ok[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const long long i = i0 + u * stride;
-            ok[u] = i < total;
-            const long long ii = ok[u] ? i : i0;
-            c8s[u] = (int)(ii % C8);
-            const long long p = ii / C8;
-            xq[u] = *reinterpret_cast<const uint4*>(x + p * xcs + c8s[u] * 8);
-            if (kRes) rq[u] = *reinterpret_cast<const uint4*>(res + p * rcs + c8s[u] * 8);
+            ok[u] = i0 + u * stride < total;
+            c8s[u] = wk.c8;
+            const long long p = wk.p;
+            wk.next();
+            if (ok[u]) {
+                xq[u] = *reinterpret_cast<const uint4*>(x + p * xcs + c8s[u] * 8);
+                if (kRes) rq[u] = *reinterpret_cast<const uint4*>(res + p * rcs + c8s[u] * 8);
+            } else {
+                xq[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (kRes) rq[u] = make_uint4(0u, 0u, 0u, 0u);
+            }
             off_y[u] = p * ycs + c8s[u] * 8;
         }
 #pragma unroll
@@ -221,16 +234,25 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_
             }
         }
         __syncthreads();
+        // flush: one 16-byte red.global.add.v4.f32 per 4 channels and accumulator. All CTAs of the grid hit the same
+        // 2*C floats, i.e. a handful of L2 slices: scalar atomics (2*C*grid = 150 k for C = 64) serialised there and
+        // cost a fixed ~20 us per launch; the vector form issues a quarter of the operations.
         if (cg < C8 && lane < lanes) {
-            for (int k = lane; k < 8; k += lanes) {
-                float t0 = 0.f, t1 = 0.f;
+            for (int h = lane; h < 2; h += lanes) {
+                float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int l = 0; l < lanes; ++l) {
-                    t0 += s_buf[((l * groups + g) * 2 + 0) * 8 + k];
-                    t1 += s_buf[((l * groups + g) * 2 + 1) * 8 + k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        t0[k] += s_buf[((l * groups + g) * 2 + 0) * 8 + h * 4 + k];
+                        t1[k] += s_buf[((l * groups + g) * 2 + 1) * 8 + h * 4 + k];
+                    }
                 }
-                const int c = cg * 8 + k;
-                atomicAdd(sum_dz + c, t0);
-                atomicAdd(sum_dz_xhat + c, __ldg(invstd + c) * (t1 - __ldg(mean + c) * t0));
+                const int c = cg * 8 + h * 4;
+                const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c));
+                const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+                red_add_v4(sum_dz + c, t0[0], t0[1], t0[2], t0[3]);
+                red_add_v4(sum_dz_xhat + c, is.x * (t1[0] - m.x * t0[0]), is.y * (t1[1] - m.y * t0[1]),
+                           is.z * (t1[2] - m.z * t0[2]), is.w * (t1[3] - m.w * t0[3]));
             }
         }
         __syncthreads();
@@ -238,7 +260,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_
 }
 
 template <int kRelu, bool kDres>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ y, int ycs,
                     const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -274,21 +296,26 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_b
     if (hoist) coeffs(threadIdx.x % C8, A, B, Cc, sc, sh);
     constexpr int kU = 2;   // two independent vectors per trip: 4-6 loads in flight per thread before the math
     const long long stride = (long long)gridDim.x * kThreads;
-    for (long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x; i0 < total; i0 += kU * stride) {
+    const long long start = (long long)blockIdx.x * kThreads + threadIdx.x;
+    VecWalk wk(C8, start, stride);
+    for (long long i0 = start; i0 < total; i0 += kU * stride) {
         uint4 gq[kU], xq[kU], yq[kU];
         long long pix[kU];
         int c8s[kU];
         bool ok[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const long long i = i0 + u * stride;
-            ok[u] = i < total;
-            const long long ii = ok[u] ? i : i0;
-            c8s[u] = (int)(ii % C8);
-            pix[u] = ii / C8;
-            gq[u] = *reinterpret_cast<const uint4*>(dy + pix[u] * dycs + c8s[u] * 8);
-            xq[u] = *reinterpret_cast<const uint4*>(x + pix[u] * xcs + c8s[u] * 8);
-            if (kRelu == 1) yq[u] = *reinterpret_cast<const uint4*>(y + pix[u] * ycs + c8s[u] * 8);
+            ok[u] = i0 + u * stride < total;
+            c8s[u] = wk.c8;
+            pix[u] = wk.p;
+            wk.next();
+            if (ok[u]) {
+                gq[u] = *reinterpret_cast<const uint4*>(dy + pix[u] * dycs + c8s[u] * 8);
+                xq[u] = *reinterpret_cast<const uint4*>(x + pix[u] * xcs + c8s[u] * 8);
+                if (kRelu == 1) yq[u] = *reinterpret_cast<const uint4*>(y + pix[u] * ycs + c8s[u] * 8);
+            } else {
+                gq[u] = xq[u] = yq[u] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -321,9 +348,11 @@ __global__ void __launch_bounds__(kThreads)
 chan_scale_fwd_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const float* __restrict__ a, float base,
                       const __nv_bfloat16* __restrict__ add, int acs, __nv_bfloat16* __restrict__ y, int ycs, int HW,
                       int C8, long long total) {
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long p = i / C8;
+    const long long stride = (long long)gridDim.x * kThreads;
+    VecWalk wk(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride);
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride, wk.next()) {
+        const int c8 = wk.c8;
+        const long long p = wk.p;
         int n = (int)(p / HW);
         float v[8], av[8];
         Vec8<__nv_bfloat16>::load(x + p * xcs + c8 * 8, v);

@@ -89,9 +89,11 @@ cast_scale_kernel(const TS* __restrict__ src, int scs, TD* __restrict__ dst, int
                   const float* __restrict__ scale_dev) {
     const float sc = scale_dev ? *scale_dev : 1.f;
     const long long total = npix * C8;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long p = i / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long p = wk_.p;
         float v[8];
         Vec8<TS>::load(src + p * scs + c8 * 8, v);
 #pragma unroll
@@ -104,9 +106,11 @@ __global__ void __launch_bounds__(kThreads)
 add_kernel(const __nv_bfloat16* __restrict__ a, int acs, const __nv_bfloat16* __restrict__ b, int bcs,
            __nv_bfloat16* __restrict__ y, int ycs, long long npix, int C8) {
     const long long total = npix * C8;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long p = i / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long p = wk_.p;
         float u[8], v[8];
         Vec8<__nv_bfloat16>::load(a + p * acs + c8 * 8, u);
         Vec8<__nv_bfloat16>::load(b + p * bcs + c8 * 8, v);
@@ -121,9 +125,11 @@ __global__ void __launch_bounds__(kThreads)
 add_relu_kernel(const __nv_bfloat16* __restrict__ a, int acs, const __nv_bfloat16* __restrict__ b, int bcs,
                 __nv_bfloat16* __restrict__ y, int ycs, long long npix, int C8) {
     const long long total = npix * C8;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long p = i / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long p = wk_.p;
         float u[8], v[8];
         Vec8<__nv_bfloat16>::load(a + p * acs + c8 * 8, u);
         Vec8<__nv_bfloat16>::load(b + p * bcs + c8 * 8, v);
@@ -138,9 +144,11 @@ __global__ void __launch_bounds__(kThreads)
 relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloat16* __restrict__ y, int ycs,
                 __nv_bfloat16* __restrict__ dx, int dxcs, long long npix, int C8) {
     const long long total = npix * C8;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long p = i / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long p = wk_.p;
         float u[8], v[8];
         Vec8<__nv_bfloat16>::load(dy + p * dycs + c8 * 8, u);
         Vec8<__nv_bfloat16>::load(y + p * ycs + c8 * 8, v);

@@ -29,9 +29,11 @@ bilinear_fwd_kernel(const TI* __restrict__ in, int ics, TO* __restrict__ out, in
                     int Ho, int Wo) {
     const float ry = area_scale(Hi, Ho), rx = area_scale(Wi, Wo);
     const long long total = (long long)N * Ho * Wo * C8;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long pix = i / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long pix = wk_.p;
         int x = (int)(pix % Wo);
         long long t = pix / Wo;
         int y = (int)(t % Ho), n = (int)(t / Ho);
@@ -87,9 +89,11 @@ bilinear_bwd_kernel(const TO* __restrict__ dout, int ocs, TI* __restrict__ din, 
     const float ry = area_scale(Hi, Ho), rx = area_scale(Wi, Wo);
     const long long total = (long long)N * Hi * Wi * C8;
     constexpr int kMaxCand = 12;  // candidate output columns kept in registers (up-scale factors >= 1/4 per side)
-    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(idx % C8);
-        long long pix = idx / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long pix = wk_.p;
         int j = (int)(pix % Wi);
         long long t = pix / Wi;
         int i = (int)(t % Hi), n = (int)(t / Hi);
@@ -205,9 +209,11 @@ __global__ void __launch_bounds__(kThreads)
 adaptive_avgpool_bwd_kernel(const float* __restrict__ dout, int N, int C8, int H, int W, int S,
                             __nv_bfloat16* __restrict__ din, int ics, int accumulate) {
     const long long total = (long long)N * H * W * C8;
-    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(idx % C8);
-        long long pix = idx / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long pix = wk_.p;
         int w = (int)(pix % W);
         long long t = pix / W;
         int h = (int)(t % H), n = (int)(t / H);
@@ -247,9 +253,11 @@ __global__ void __launch_bounds__(kThreads)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ics, __nv_bfloat16* __restrict__ out, int ocs,
                    uint8_t* __restrict__ idx, int N, int C8, int H, int W, int P, int Q) {
     const long long total = (long long)N * P * Q * C8;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long pix = i / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long pix = wk_.p;
         int q = (int)(pix % Q);
         long long t = pix / Q;
         int p = (int)(t % P), n = (int)(t / P);
@@ -290,9 +298,11 @@ maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restr
                    __nv_bfloat16* __restrict__ din, int dcs, int N, int C8, int H, int W, int P, int Q) {
     const int HB = (H + 1) / 2, WB = (W + 1) / 2;
     const long long total = (long long)N * HB * WB * C8;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-        int c8 = (int)(i % C8);
-        long long blk = i / C8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);   // no 64-bit division per vector
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long blk = wk_.p;
         int b = (int)(blk % WB);
         long long t = blk / WB;
         int a = (int)(t % HB), n = (int)(t / HB);
