@@ -195,6 +195,10 @@ int tsb_unpack_stem_wgrad(const float* dwp, int K, int R, float* dw, tsb_stream_
 /* elementwise: dst = (dtype)src * (*scale_dev or 1) ; strided NHWC channel slices, C multiple of 8 */
 int tsb_cast_scale(const void* src, int sdtype, int scs, void* dst, int ddtype, int dcs, long long npix, int C,
                    const float* scale_dev, tsb_stream_t stream);
+/* dst[pix, 0..Kp) = (bf16) src[pix, 0..K) zero-extended (any K, any source channel stride): the gradient of a K-class
+ * head into the 64-multiple GEMM-K layout tsb_conv2d_dgrad / wgrad read */
+int tsb_cast_pad(const void* src, int sdtype, int scs, int K, void* dst_bf16, int dcs, int Kp, long long npix,
+                 tsb_stream_t stream);
 /* y = a + b (bf16 NHWC) */
 int tsb_add(const void* a, int acs, const void* b, int bcs, void* y, int ycs, long long npix, int C,
             tsb_stream_t stream);

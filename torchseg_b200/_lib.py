@@ -56,6 +56,7 @@ _SIGS = {
     "tsb_unpack_stem_wgrad": [P, I, I, P, P],
     "tsb_cast_scale": [P, I, I, P, I, I, L, I, P, P],
     "tsb_add": [P, I, P, I, P, I, L, I, P],
+    "tsb_cast_pad": [P, I, I, I, P, I, I, L, P],
     "tsb_add_relu": [P, I, P, I, P, I, L, I, P],
     "tsb_softmax_rows_fwd": [P, I, I, P, I, L, I, I, P],
     "tsb_softmax_rows_bwd": [P, I, P, I, P, I, L, I, I, P],

@@ -357,16 +357,34 @@ __global__ void __launch_bounds__(kThreads) ohem_loss_kernel(const float* __rest
     const bool active = state[ST_ACTIVE] != 0;
     const float T = __uint_as_float(state[ST_THRESH]);
     float ls = 0.f, ws = 0.f, kc = 0.f;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-        long long lab = labels[i];
-        bool kept = (lab != (long long)ignore_label) && (!active || p[i] <= T);
+    auto one = [&](long long lab, float pv, float nl) {
+        const bool kept = (lab != (long long)ignore_label) && (!active || pv <= T);
         if (kept) {
-            float wt = cw ? __ldg(cw + (int)lab) : 1.f;
-            ls += wt * nll[i];
+            const float wt = cw ? __ldg(cw + (int)lab) : 1.f;
+            ls += wt * nl;
             ws += wt;
             kc += 1.f;
         }
+    };
+    // four pixels per thread and trip: 2 x 16 B of labels + 16 B of p + 16 B of nll in flight per thread
+    const long long n4 = n / 4;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(nll) | reinterpret_cast<uintptr_t>(labels)) & 15u) == 0;
+    long long done = 0;
+    if (vec_ok) {
+        for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < n4; q += (long long)gridDim.x * kThreads) {
+            const longlong2 l01 = *reinterpret_cast<const longlong2*>(labels + q * 4);
+            const longlong2 l23 = *reinterpret_cast<const longlong2*>(labels + q * 4 + 2);
+            const float4 pv = *reinterpret_cast<const float4*>(p + q * 4);
+            const float4 nv = *reinterpret_cast<const float4*>(nll + q * 4);
+            one(l01.x, pv.x, nv.x);
+            one(l01.y, pv.y, nv.y);
+            one(l23.x, pv.z, nv.z);
+            one(l23.y, pv.w, nv.w);
+        }
+        done = n4 * 4;
     }
+    for (long long i = done + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads)
+        one(labels[i], p[i], nll[i]);
     ls = block_sum<kThreads>(ls, s_red);
     ws = block_sum<kThreads>(ws, s_red);
     kc = block_sum<kThreads>(kc, s_red);

@@ -158,6 +158,25 @@ relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, const __nv_bfloa
     }
 }
 
+// dst[pix, 0..Kp) (bf16) = src[pix, 0..K) zero-extended: gradient of a K-class head (K = 19, 150, 1 ...) into the
+// 64-multiple GEMM-K layout the dgrad / wgrad kernels read. Any K, any source channel stride; one pass, no memset.
+template <typename TS>
+__global__ void __launch_bounds__(kThreads)
+cast_pad_kernel(const TS* __restrict__ src, int scs, int K, __nv_bfloat16* __restrict__ dst, int dcs, int Kp8,
+                long long npix) {
+    const long long total = npix * Kp8;
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(Kp8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
+        const int c0 = wk_.c8 * 8;
+        const TS* s = src + wk_.p * scs + c0;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (c0 + k < K) ? (float)s[k] : 0.f;
+        Vec8<__nv_bfloat16>::store(dst + wk_.p * dcs + c0, v);
+    }
+}
+
 // db[k] += Σ_pix dy[pix,k]; one warp per pixel stripe, lanes over channels (K <= 64 typical: 19 padded)
 __global__ void __launch_bounds__(kThreads)
 bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, int dycs, long long npix, int K, float* __restrict__ db) {
@@ -339,6 +358,20 @@ extern "C" int tsb_cast_scale(const void* src, int sdtype, int scs, void* dst, i
     else TSB_FAIL(TSB_ERR_ARG, "tsb_cast_scale: bad dtype");
 #undef L
     TSB_CUDA_CHECK_LAUNCH("cast_scale");
+    return TSB_OK;
+}
+
+extern "C" int tsb_cast_pad(const void* src, int sdtype, int scs, int K, void* dst_bf16, int dcs, int Kp, long long npix,
+                            tsb_stream_t stream) {
+    TSB_REQUIRE(src && dst_bf16 && npix > 0 && K > 0 && Kp >= K, "tsb_cast_pad: bad args");
+    TSB_REQUIRE(Kp % 8 == 0 && dcs % 8 == 0 && dcs >= Kp && scs >= K && tsb_aligned16(dst_bf16), "tsb_cast_pad: Kp, dcs multiples of 8");
+    TSB_REQUIRE(sdtype == TSB_F32 || sdtype == TSB_BF16, "tsb_cast_pad: bad dtype");
+    int grid = tsb_grid_for(npix * (Kp / 8), kThreads, 8);
+    if (sdtype == TSB_F32)
+        cast_pad_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float*)src, scs, K, (__nv_bfloat16*)dst_bf16, dcs, Kp / 8, npix);
+    else
+        cast_pad_kernel<__nv_bfloat16><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, scs, K, (__nv_bfloat16*)dst_bf16, dcs, Kp / 8, npix);
+    TSB_CUDA_CHECK_LAUNCH("cast_pad");
     return TSB_OK;
 }
 

@@ -5,6 +5,24 @@
 #include "nhwc_vec.cuh"
 
 namespace {
+
+// pixel index → (n, row, col). One 64-bit division costs ~100 issue slots; activations have < 2^31 pixels, so the
+// common case runs on 32-bit unsigned divisions.
+__device__ __forceinline__ void split_pix(long long pix, int W, int H, int& w, int& h, int& n) {
+    if (pix < 0x7fffffffLL) {
+        const unsigned u = (unsigned)pix;
+        const unsigned t = u / (unsigned)W;
+        w = (int)(u - t * (unsigned)W);
+        const unsigned nn = t / (unsigned)H;
+        h = (int)(t - nn * (unsigned)H);
+        n = (int)nn;
+    } else {
+        w = (int)(pix % W);
+        const long long t = pix / W;
+        h = (int)(t % H);
+        n = (int)(t / H);
+    }
+}
 constexpr int kThreads = 256;
 
 __host__ __device__ __forceinline__ float area_scale(int in_size, int out_size) {
@@ -34,9 +52,8 @@ bilinear_fwd_kernel(const TI* __restrict__ in, int ics, TO* __restrict__ out, in
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
         const int c8 = wk_.c8;
         const long long pix = wk_.p;
-        int x = (int)(pix % Wo);
-        long long t = pix / Wo;
-        int y = (int)(t % Ho), n = (int)(t / Ho);
+        int x, y, n;
+        split_pix(pix, Wo, Ho, x, y, n);
         Lerp ly = make_lerp(ry, y, Hi), lx = make_lerp(rx, x, Wi);
         const TI* b = in + (long long)n * Hi * Wi * ics + c8 * 8;
         float a[8], bb[8], c[8], d[8], o[8];
@@ -94,9 +111,8 @@ bilinear_bwd_kernel(const TO* __restrict__ dout, int ocs, TI* __restrict__ din, 
     for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += stride_, wk_.next()) {
         const int c8 = wk_.c8;
         const long long pix = wk_.p;
-        int j = (int)(pix % Wi);
-        long long t = pix / Wi;
-        int i = (int)(t % Hi), n = (int)(t / Hi);
+        int j, i, n;
+        split_pix(pix, Wi, Hi, j, i, n);
         int y_lo, y_hi, x_lo, x_hi;
         if (ry > 0.f) { y_lo = max(0, (int)floorf((float)(i - 1) / ry) - 1); y_hi = min(Ho - 1, (int)ceilf((float)(i + 1) / ry) + 1); }
         else { y_lo = 0; y_hi = Ho - 1; }
@@ -214,9 +230,8 @@ adaptive_avgpool_bwd_kernel(const float* __restrict__ dout, int N, int C8, int H
     for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += stride_, wk_.next()) {
         const int c8 = wk_.c8;
         const long long pix = wk_.p;
-        int w = (int)(pix % W);
-        long long t = pix / W;
-        int h = (int)(t % H), n = (int)(t / H);
+        int w, h, n;
+        split_pix(pix, W, H, w, h, n);
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -258,9 +273,8 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ics, __nv_bfloat16*
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
         const int c8 = wk_.c8;
         const long long pix = wk_.p;
-        int q = (int)(pix % Q);
-        long long t = pix / Q;
-        int p = (int)(t % P), n = (int)(t / P);
+        int q, p, n;
+        split_pix(pix, Q, P, q, p, n);
         float m[8];
         uint32_t am[8];
 #pragma unroll
@@ -303,9 +317,8 @@ maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restr
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride_, wk_.next()) {
         const int c8 = wk_.c8;
         const long long blk = wk_.p;
-        int b = (int)(blk % WB);
-        long long t = blk / WB;
-        int a = (int)(t % HB), n = (int)(t / HB);
+        int b, a, n;
+        split_pix(blk, WB, HB, b, a, n);
         uint2 pk[4];
         uint4 gv[4];
         bool ok[4];

@@ -542,10 +542,11 @@ class ConvFn(torch.autograd.Function):
         if dy.dtype == _BF and dy.stride(1) == 1 and cs_of(dy) >= Kp and K == Kp:
             dyb = dy
         else:
-            dyb = nhwc_zeros(N, Kp, P, Q, device=dev)
-            if dy.stride(1) == 1 and K % 8 == 0:
-                call("tsb_cast_scale", ptr(dy), _lib.dt(dy), cs_of(dy), ptr(dyb), BF16, Kp, N * P * Q, K, None, stream())
+            if dy.stride(1) == 1 and dy.dtype in (_BF, torch.float32):
+                dyb = nhwc_empty(N, Kp, P, Q, device=dev)     # tsb_cast_pad writes all Kp channels (zero pads)
+                call("tsb_cast_pad", ptr(dy), _lib.dt(dy), cs_of(dy), K, ptr(dyb), Kp, Kp, N * P * Q, stream())
             else:
+                dyb = nhwc_zeros(N, Kp, P, Q, device=dev)
                 dyb[:, :K].copy_(dy)
         direct = _direct_grad(w) and (not has_bias or _direct_grad(ctx.bias_ref))
         if direct:
