@@ -25,6 +25,10 @@ CASES = [
     (1, 64, 7, 260, 128, 3, 2, 1, 1),      # row tiles, stride 2 (parity views), Q = 130
     (1, 64, 3, 300, 64, 3, 1, 4, 4),       # row tiles + dilation 4 (span 8)
     (1, 128, 4, 256, 64, 1, 1, 0, 1),      # 1x1 → flat GEMM, resident weights
+    # >= 2 tiles per CTA with streamed weights → weight-sharing tile PAIRS (two accumulators per B tile), odd tails
+    (8, 128, 64, 128, 128, 3, 1, 1, 1),    # 512 row tiles over 148 CTAs (3 or 4 each)
+    (4, 128, 40, 136, 256, 3, 1, 2, 2),    # two N tiles, dilation 2, ragged width (2 tiles per row)
+    (4, 1024, 48, 128, 256, 1, 1, 0, 1),   # 1x1 with streamed weights (flat GEMM), 4 stages
 ]
 
 

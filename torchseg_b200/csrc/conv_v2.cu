@@ -48,7 +48,11 @@ struct alignas(64) V2Params {
     int nstages, stage_bytes, res_bytes, use_base_offset;
 };
 
-template <int BN, bool RES>
+// PAIR (streamed B, BN = 128 only): two pixel tiles share every weight tile — one stage carries two A boxes and the B
+// taps, the issuer runs the MMAs of both tiles against the same B operand (four TMEM accumulators, 512 columns). The
+// L2→SM traffic per FLOP of the weight-streaming layers drops ~37 % (3x3: 82 KB per 12.6 MFLOP instead of 65 KB per
+// 6.3); at the measured ~43 B/clk/SM of TMA ingest that traffic, not the tensor pipe, bounds these layers.
+template <int BN, bool RES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_constant__ V2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
         mbar_init(b_ready, 1);
         fence_barrier_init();
     } else if (warp == 2) {
-        tmem_alloc<2 * BN>(tmem_ptr);
+        tmem_alloc<(PAIR ? 4 : 2) * BN>(tmem_ptr);
         for (int i = lane; i < 2 * BN; i += 32) s_stats[i] = 0.f;
     }
     tc_fence_before();
@@ -96,6 +100,37 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                             tma_load_2d(res_b + (p.groups[g].tap_idx[t] * p.kchunks + kc) * kBTile, &p.mapB, b_ready,
                                         p.groups[g].bk[t] + kc * 64, n0);
             }
+            if (PAIR) {
+                // one ring; pair j = local tiles (2j, 2j+1): A0 | A1 | B taps per stage
+                int sl = 0;
+                uint32_t ph = 0;
+                const int npairs = (my_tiles + 1) >> 1;
+                for (int j = 0; j < npairs; ++j) {
+                    int q0[2], p0[2], nimg[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int li = (2 * j + u < my_tiles) ? 2 * j + u : 2 * j;   // odd tail: duplicate tile, never stored
+                        const int tile = blockIdx.x + li * gridDim.x;
+                        q0[u] = (tile % p.tiles_w) * p.TW;
+                        p0[u] = ((tile / p.tiles_w) % p.tiles_h) * p.TH;
+                        nimg[u] = tile / (p.tiles_w * p.tiles_h);
+                    }
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        const int gmap = p.groups[g].map, ntaps = p.groups[g].ntaps;
+                        const uint32_t bytes = 2u * (uint32_t)p.a_bytes[gmap] + (uint32_t)(ntaps * kBTile);
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(&empty_bar[sl], ph ^ 1u);
+                            uint8_t* a_s = stages + sl * p.stage_bytes;
+                            mbar_arrive_expect_tx(&full_bar[sl], bytes);
+                            tma_load_4d(a_s, &p.mapA[gmap], &full_bar[sl], kc * 64, q0[0] + p.groups[g].dw0, p0[0] + p.groups[g].dh, nimg[0]);
+                            tma_load_4d(a_s + kAStageBytes, &p.mapA[gmap], &full_bar[sl], kc * 64, q0[1] + p.groups[g].dw0, p0[1] + p.groups[g].dh, nimg[1]);
+                            for (int t = 0; t < ntaps; ++t)
+                                tma_load_2d(a_s + 2 * kAStageBytes + t * kBTile, &p.mapB, &full_bar[sl], p.groups[g].bk[t] + kc * 64, n0);
+                            if (++sl == p.nstages) { sl = 0; ph ^= 1u; }
+                        }
+                    }
+                }
+            } else {
             // two stage rings (one per MMA-issuing thread) when there are >= 4 stages: tile i uses ring i & 1
             const bool dual_p = p.nstages >= 4;
             const int half_p = dual_p ? p.nstages / 2 : p.nstages;
@@ -130,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                 }
                 if (r1) { cs1 = sl; cp1 = ph; } else { cs0 = sl; cp0 = ph; }
             }
+            }  // !PAIR
         }
     } else if (warp == 1 || warp == 3) {
         // TWO MMA-issuing threads (one elected lane each): warp 1 takes the even local tiles (TMEM buffer 0), warp 3
@@ -137,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
         // the per-MMA work is reduced to two 64-bit descriptor adds.
         // Each issuing thread owns its own stage ring (single producer / single consumer per ring), so the mbarrier
         // parity waits can never alias an older phase whatever the K-loop length. With < 4 stages warp 1 works alone.
-        const bool dual = p.nstages >= 4;
+        const bool dual = !PAIR && p.nstages >= 4;
         const int half = dual ? p.nstages / 2 : p.nstages;
         const int par = (warp == 3) ? 1 : 0;
         const int tstep = dual ? 2 : 1;
@@ -151,6 +187,44 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
             const int sbase = (dual && par) ? half : 0;
             int sl = 0;
             uint32_t ph = 0;
+            if (PAIR) {
+                const int npairs = (my_tiles + 1) >> 1;
+                for (int j = 0; j < npairs; ++j) {
+                    const int pb = j & 1;
+                    mbar_wait(&tmem_empty[pb], (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue drained both tiles of pair j-2
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + (uint32_t)(pb * 2) * BN, d1 = d0 + BN;
+                    uint32_t acc = 0;
+                    for (int g = 0; g < p.ngroups; ++g) {
+                        const int ntaps = p.groups[g].ntaps;
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(&full_bar[sl], ph);
+                            tc_fence_after();
+                            const uint32_t a_lo = (stages_u32 + (uint32_t)(sl * p.stage_bytes)) >> 4;
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {
+                                if (t < ntaps) {
+                                    const uint64_t da0 = desc_hi | (uint64_t)(a_lo + (uint32_t)p.groups[g].row_off[t] * 8u);
+                                    const uint64_t da1 = da0 + (uint64_t)(kAStageBytes >> 4);
+                                    const uint64_t db = desc_hi | (uint64_t)(a_lo + (uint32_t)((2 * kAStageBytes + t * kBTile) >> 4));
+                                    umma_bf16(d0, da0, db, idesc, acc);
+                                    umma_bf16(d0, da0 + 2, db + 2, idesc, 1u);
+                                    umma_bf16(d0, da0 + 4, db + 4, idesc, 1u);
+                                    umma_bf16(d0, da0 + 6, db + 6, idesc, 1u);
+                                    umma_bf16(d1, da1, db, idesc, acc);
+                                    umma_bf16(d1, da1 + 2, db + 2, idesc, 1u);
+                                    umma_bf16(d1, da1 + 4, db + 4, idesc, 1u);
+                                    umma_bf16(d1, da1 + 6, db + 6, idesc, 1u);
+                                    acc = 1u;
+                                }
+                            }
+                            umma_commit(&empty_bar[sl]);
+                            if (++sl == p.nstages) { sl = 0; ph ^= 1u; }
+                        }
+                    }
+                    umma_commit(&tmem_full[pb]);
+                }
+            } else {
             for (int i = par; i < my_tiles; i += tstep) {
                 const int buf = i & 1;
                 mbar_wait(&tmem_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
@@ -184,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                 }
                 umma_commit(&tmem_full[buf]);
             }
+            }  // !PAIR
         }
     } else if (warp >= 4) {
         // 8 epilogue warps. TMEM lane quarter = warp % 4 (hardware rule); the column range is split by (warp-4)/4:
@@ -208,12 +283,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
             const bool valid = (pp < p.P) && (qq < p.Q);
             const long long pix_off = p.out_base + (long long)n_img * p.out_n_stride + (long long)pp * p.out_p_stride +
                                       (long long)qq * p.out_q_stride;
-            const int buf = i & 1;
-            if (iters_per_tile > 0) {
-                mbar_wait(&tmem_full[buf], ((uint32_t)i >> 1) & 1u);
+            // PAIR: accumulator (i & 3) of four, full/empty barriers per pair; otherwise buffer i & 1 of two
+            const int buf = PAIR ? ((i >> 1) & 1) : (i & 1);
+            const int acc_slot = PAIR ? (((i >> 1) & 1) * 2 + (i & 1)) : (i & 1);
+            const bool wait_full = PAIR ? ((i & 1) == 0) : true;
+            const bool last_of_buf = PAIR ? ((i & 1) == 1 || i == my_tiles - 1) : true;
+            if (iters_per_tile > 0 && wait_full) {
+                mbar_wait(&tmem_full[buf], (PAIR ? ((uint32_t)i >> 2) : ((uint32_t)i >> 1)) & 1u);
                 tc_fence_after();
             }
-            const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t taddr = tmem_base + acc_slot * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
             for (int jj = 0; jj < kChunksPerWarp; ++jj) {
                 const int j = chalf * kChunksPerWarp + jj;
@@ -225,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
 #pragma unroll
                     for (int q = 0; q < 32; ++q) r[q] = 0u;
                 }
-                if (jj == kChunksPerWarp - 1) {  // this warp's TMEM reads of the tile are done
+                if (jj == kChunksPerWarp - 1 && last_of_buf) {  // this warp's TMEM reads of the tile (pair) are done
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -335,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<2 * BN>(tmem_base);
+        tmem_dealloc<(PAIR ? 4 : 2) * BN>(tmem_base);
     }
 }
 
@@ -473,15 +552,16 @@ int g_use_base_offset = 0;  // measured on B200: the swizzle XOR is taken from t
 int g_allow_rows = 1;
 int g_allow_resident = 1;
 int g_wgrad_waves = 2;
+int g_allow_pair = 1;   // tsb_debug_set key 7: weight-sharing tile pairs in the streamed BN = 128 conv kernel
 
-template <int BN, bool RES>
+template <int BN, bool RES, bool PAIR = false>
 int launch_v2(const V2Params& prm, int grid_x, int n_tiles, size_t smem, cudaStream_t st) {
     static size_t attr_bytes = 0;
     if (smem > attr_bytes) {
-        TSB_CUDA_CALL(cudaFuncSetAttribute(igemm_v2_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TSB_CUDA_CALL(cudaFuncSetAttribute(igemm_v2_kernel<BN, RES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_bytes = 227 * 1024;
     }
-    igemm_v2_kernel<BN, RES><<<dim3(grid_x, n_tiles), kThreads, smem, st>>>(prm);
+    igemm_v2_kernel<BN, RES, PAIR><<<dim3(grid_x, n_tiles), kThreads, smem, st>>>(prm);
     TSB_CUDA_CHECK_LAUNCH("igemm_v2");
     return TSB_OK;
 }
@@ -496,6 +576,7 @@ extern "C" int tsb_debug_set(int key, int value) {
     else if (key == 4) convv2::g_enabled = value;
     else if (key == 5) { g_wgrad_waves = value; convv2::g_wgrad_waves_x = value; }
     else if (key == 6) g_tsb_ohem_hoist = value;
+    else if (key == 7) g_allow_pair = value;
     else return TSB_ERR_ARG;
     return TSB_OK;
 }
@@ -596,7 +677,11 @@ int launch(const Desc& d, cudaStream_t st) {
     int max_group_taps = 1;
     for (int g = 0; g < ng; ++g) if (prm.groups[g].ntaps > max_group_taps) max_group_taps = prm.groups[g].ntaps;
     prm.res_bytes = resident ? (int)res_need : 0;
-    prm.stage_bytes = kAStageBytes + (resident ? 0 : max_group_taps * kBTile);
+    int grid_pre = tsb_num_sms() / n_tiles;
+    if (grid_pre < 1) grid_pre = 1;
+    // pair mode: streamed weights, BN = 128, at least two tiles per CTA (otherwise the second accumulator idles)
+    const bool pair = g_allow_pair && !resident && BN == 128 && prm.m_tiles >= 2 * grid_pre;
+    prm.stage_bytes = (pair ? 2 : 1) * kAStageBytes + (resident ? 0 : max_group_taps * kBTile);
     int ns = (budget - prm.res_bytes) / prm.stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;
     TSB_REQUIRE(ns >= 2, "conv_v2: shared-memory plan needs at least 2 stages");
@@ -607,6 +692,7 @@ int launch(const Desc& d, cudaStream_t st) {
     if (grid_x > prm.m_tiles) grid_x = prm.m_tiles;
     if (grid_x < 1) grid_x = 1;
     if (BN == 64) return resident ? launch_v2<64, true>(prm, grid_x, n_tiles, smem, st) : launch_v2<64, false>(prm, grid_x, n_tiles, smem, st);
+    if (pair) return launch_v2<128, false, true>(prm, grid_x, n_tiles, smem, st);
     return resident ? launch_v2<128, true>(prm, grid_x, n_tiles, smem, st) : launch_v2<128, false>(prm, grid_x, n_tiles, smem, st);
 }
 
