@@ -316,3 +316,25 @@ def test_focal_loss(cuda):
     ld.backward()
     assert abs(ld.item() - lr.item()) < 1e-4 * abs(lr.item())
     assert rel_err(pd.grad, pr.grad) < 1e-3
+
+
+def test_cuda_prefetcher_delivers_batches_in_order(cuda):
+    """CudaPrefetcher (double-buffered H2D on a side stream, train.py:119-124): every batch arrives intact and in order
+    even when the consumer launches work that is still running while the next copy is issued"""
+    from torchseg_b200.utils.prefetch import CudaPrefetcher
+    g = torch.Generator().manual_seed(31)
+    host = [{"data": torch.randn(4, 3, 64, 96, generator=g).pin_memory(),
+             "label": torch.randint(0, 19, (4, 64, 96), generator=g).pin_memory(), "fn": "img%d" % i} for i in range(7)]
+    loader = CudaPrefetcher(iter(host), cuda)
+    seen = 0
+    big = torch.randn(4096, 4096, device=cuda)
+    for i, mb in enumerate(loader):
+        acc = big @ big                      # keep the compute stream busy while the next batch is copied
+        s = mb["data"].double().sum() + mb["label"].double().sum()
+        ref = host[i]["data"].double().sum() + host[i]["label"].double().sum()
+        assert mb["fn"] == "img%d" % i
+        assert abs(float(s) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+        assert torch.equal(mb["label"].cpu(), host[i]["label"])
+        seen += 1
+        del acc
+    assert seen == 7

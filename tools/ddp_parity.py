@@ -46,4 +46,5 @@ if rank == 0:
     print("ranks identical:", same, "| mean loss 2x8:", float(gl), "single 16:", float(l1), "| rel param diff after step %.3e" % float(d))
     assert same
     assert abs(float(gl) - float(l1)) < 2e-2 * abs(float(l1))
+    print("OK")
 dist.barrier(); dist.destroy_process_group()
