@@ -254,6 +254,7 @@ def main():
                     help="bisenet = BASELINE configs[1] (the metric); pspnet / dfn = secondary lines (SURVEY C3 / C4)")
     ap.add_argument("--size", type=int, default=0, help="input size override (pspnet default 480, the reference shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -309,11 +310,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def set_lr(it_):
+        lr = lr_policy.get_lr(it_)
+        for i, g in enumerate(opt.param_groups):
+            g['lr'] = lr if i < 2 else lr * 10  # train.py:136-139
+
     it = 0
     for _ in range(warmup):
         loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
         it += 1
-    # ---------------- timed region 1: inputs resident in HBM; conv launches bracketed by CUDA events
+    # ---------------- measurement pass A (eager launches): every conv launch bracketed by CUDA events on the launch
+    # stream → roofline.achieved; also the throughput of the un-graphed step
     ops.conv_prof.enable()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -326,10 +333,48 @@ def main():
         e1.record()
         barrier()
     launches = _lib.launch_count() - launches0
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_eager = max_over_ranks(e0.elapsed_time(e1))
+    ms = ms_eager
     prof = ops.conv_prof.collect()
     ops.conv_prof.disable()
     final_loss = float(loss.item())
+    # ---------------- timed region 1 (`value`): the same step as ONE CUDA graph (single GPU; zero_grad → forward →
+    # backward → fused SGD captured once, torchseg_b200.engine.graph.GraphedTrainStep), inputs resident in HBM.
+    # Falls back to the eager numbers above when capture is unavailable (multi-GPU: the DDP side stream is not captured).
+    gstep = None
+    if world == 1 and not args.no_graph:
+        from torchseg_b200.engine.graph import GraphedTrainStep
+        set_lr(it)
+        gstep = GraphedTrainStep(model, opt, dev_batch, warmup=2)
+        if gstep.graph is None:
+            sys.stderr.write("bench: CUDA graph capture unavailable (%s); eager step timed instead\n" % gstep.error)
+            gstep = None
+    if gstep is not None:
+        static_in = gstep.static_inputs
+        for _ in range(2):
+            set_lr(it)
+            loss = gstep(*static_in)
+            it += 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record()
+            for _ in range(args.steps):
+                set_lr(it)
+                loss = gstep(*static_in)      # inputs already in the graph's static buffers: no copy
+                it += 1
+            e1.record()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = gstep.launches_per_step * args.steps
+        final_loss = float(loss.item())
+
+    def run_step(it_, *inputs):
+        if gstep is not None:
+            set_lr(it_)
+            return gstep(*inputs)
+        return train_step(model, ddp, opt, lr_policy, it_, *inputs)
+
     # ---------------- timed region 2: end to end through the public API with HOST buffers: every step's inputs are
     # copied from pinned host memory (CudaPrefetcher: side-stream copy of batch i+1 under step i) and every step's
     # loss is read back to the host (async D2H into pinned memory, value consumed one step later)
@@ -344,14 +389,14 @@ def main():
     # exactly one H2D batch copy is issued per step (the copy of step i+1 overlaps the compute of step i)
     loader = CudaPrefetcher(host_batches(args.steps + 2), device)
     mb = loader.next()
-    train_step(model, ddp, opt, lr_policy, it, *[mb[k] for k in keys])
+    run_step(it, *[mb[k] for k in keys])
     it += 1
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for k in range(args.steps):
         mb = loader.next()                                       # train.py:119-124
-        loss = train_step(model, ddp, opt, lr_policy, it, *[mb[k] for k in keys])
+        loss = run_step(it, *[mb[k_] for k_ in keys])
         it += 1
         loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # train.py:146 (per-iteration loss read)
     e3.record()
@@ -382,6 +427,8 @@ def main():
                        "sync_bn": world > 1, "optimizer": "fused flat SGD (momentum 0.9, poly LR, reference wd / lr groups)",
                        "l2_policy": "inputs larger than L2 (activations >> 126 MB per step), no explicit flush",
                        "final_loss": final_loss,
+                       "step_launch": ("one CUDA graph replay per step (GraphedTrainStep)" if gstep is not None else "eager launches"),
+                       "eager_ms_per_step": ms_eager / args.steps,
                        "step_conv_gflop_per_img": STEP_GFLOP_PER_IMG,
                        "frac_of_conv_flop_roofline": value / world * STEP_GFLOP_PER_IMG / 1e3 / peaks["tflops"]},
             "e2e": {"value": e2e_v, "unit": "images/sec",

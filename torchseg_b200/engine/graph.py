@@ -1,0 +1,63 @@
+"""Whole-step CUDA graph for the train loop (zero_grad → forward(loss) → backward → fused SGD step).
+
+The step of /root/reference/model/bisenet/cityscapes.bisenet.R18/train.py:116-142 is ~400 kernel launches of 5-200 us
+each; captured once, a replay removes the per-launch CPU work (Python autograd, ctypes, tensor-map encoding) and the
+inter-kernel launch gaps. Single process / single GPU only (the DDP side-stream all-reduce is not captured).
+
+Usage:
+    step = GraphedTrainStep(model, optimizer, example_inputs)     # runs `warmup` eager steps, then captures
+    for it, batch in enumerate(loader):
+        set the learning rates in optimizer.param_groups as usual
+        loss = step(batch['data'], batch['label'])                # device tensors; copied into the static inputs
+If capture is impossible (non-CUDA device, an op that cannot be captured) the object silently runs eager steps."""
+import torch
+
+
+class GraphedTrainStep(object):
+    def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True):
+        self.model = model
+        self.opt = optimizer
+        self.static_inputs = [t.clone() for t in example_inputs]
+        self.graph = None
+        self.static_loss = None
+        self.launches_per_step = 0
+        self.error = None
+        dev = self.static_inputs[0].device
+        if not enable or dev.type != "cuda":
+            return
+        from .. import _lib
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):          # allocator pools, lazy attributes, FlatPack mirror all warm
+                    self._eager(*self.static_inputs)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                self.static_loss = self._eager(*self.static_inputs)
+            self.launches_per_step = _lib.launch_count() - n0
+            self.graph = g
+        except Exception as e:  # noqa: BLE001 — fall back to eager steps, keep the reason
+            self.error = "%s: %s" % (type(e).__name__, e)
+            self.graph = None
+            torch.cuda.synchronize(dev)
+
+    def _eager(self, *inputs):
+        self.opt.zero_grad()
+        loss = self.model(*inputs)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def __call__(self, *inputs):
+        if self.graph is None:
+            return self._eager(*inputs)
+        for dst, src in zip(self.static_inputs, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.opt.stage_hyperparams()
+        self.graph.replay()
+        return self.static_loss
