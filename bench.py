@@ -319,29 +319,13 @@ def main():
     for _ in range(warmup):
         loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
         it += 1
-    # ---------------- measurement pass A (eager launches): every conv launch bracketed by CUDA events on the launch
-    # stream → roofline.achieved; also the throughput of the un-graphed step
-    ops.conv_prof.enable()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count()
-    with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
-            it += 1
-        e1.record()
-        barrier()
-    launches = _lib.launch_count() - launches0
-    ms_eager = max_over_ranks(e0.elapsed_time(e1))
-    ms = ms_eager
-    prof = ops.conv_prof.collect()
-    ops.conv_prof.disable()
-    final_loss = float(loss.item())
     # ---------------- timed region 1 (`value`): the same step as ONE CUDA graph (single GPU; zero_grad → forward →
     # backward → fused SGD captured once, torchseg_b200.engine.graph.GraphedTrainStep), inputs resident in HBM.
     # Falls back to the eager numbers above when capture is unavailable (multi-GPU: the DDP side stream is not captured).
+    # (captured BEFORE the event-instrumented eager pass: a capture attempted after that pass is invalidated on this
+    # stack — tools/diag_graph2.py)
     gstep = None
+    ms = None
     if world == 1 and not args.no_graph:
         from torchseg_b200.engine.graph import GraphedTrainStep
         set_lr(it)
@@ -366,9 +350,31 @@ def main():
             e1.record()
             barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        launches = gstep.launches_per_step * args.steps
+        launches_graph = gstep.launches_per_step * args.steps
         final_loss = float(loss.item())
 
+    # ---------------- measurement pass A (eager launches): every conv launch bracketed by CUDA events on the launch
+    # stream → roofline.achieved; also the throughput of the un-graphed step
+    ops.conv_prof.enable()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk_eager:
+        e0.record()
+        for _ in range(args.steps):
+            loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
+            it += 1
+        e1.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms_eager = max_over_ranks(e0.elapsed_time(e1))
+    launches_eager = launches
+    prof = ops.conv_prof.collect()
+    ops.conv_prof.disable()
+    if ms is None:      # no graph: the eager pass IS timed region 1
+        ms, clk, final_loss = ms_eager, clk_eager, float(loss.item())
+    else:
+        launches = launches_graph
     def run_step(it_, *inputs):
         if gstep is not None:
             set_lr(it_)

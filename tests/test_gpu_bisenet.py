@@ -374,38 +374,63 @@ def test_graphed_train_step_matches_eager(cuda):
     def make():
         model, sd, x, y, _ = _build(cuda, N=4, HW=128, seed=7)
         groups = group_weight([], model, BN, 1e-2)
-        return model, optim.SGD(groups, lr=1e-2, momentum=0.9, weight_decay=5e-4), x.to(cuda), y.to(cuda)
+        g2 = torch.Generator().manual_seed(99)
+        x2 = torch.randn(x.shape, generator=g2)
+        y2 = make_labels(4, 128, 128, 19, 255, g2)
+        data = [(x.to(cuda), y.to(cuda)), (x2.to(cuda), y2.to(cuda))]     # two different batches, alternating
+        return model, optim.SGD(groups, lr=1e-2, momentum=0.9, weight_decay=5e-4), data
 
     lrs = [1e-2, 1e-2, 8e-3, 6e-3, 0.0, 0.0]
     # eager reference trajectory
-    model, opt, x, y = make()
+    model, opt, data = make()
     eager = []
-    for lr in lrs:
+    for k, lr in enumerate(lrs):
         for g in opt.param_groups:
             g["lr"] = lr
         opt.zero_grad()
-        loss = model(x, y)
+        loss = model(*data[k & 1])
         loss.backward()
         opt.step()
         eager.append(loss.item())
-    # graphed: 2 warm-up steps inside the constructor (lr of steps 0, 1), then replays
-    model, opt, x, y = make()
-    for g in opt.param_groups:
-        g["lr"] = lrs[0]
-    step = GraphedTrainStep(model, opt, [x, y], warmup=2)
+    # graphed: the constructor runs two eager warm-up steps on its static inputs (= trajectory steps 0 and 1 must see
+    # batches 0 and 1, so warm up by hand and capture with warmup=0)
+    model, opt, data = make()
+    for k in (0, 1):
+        for g in opt.param_groups:
+            g["lr"] = lrs[k]
+        opt.zero_grad()
+        loss = model(*data[k & 1])
+        loss.backward()
+        opt.step()
+    step = GraphedTrainStep(model, opt, list(data[0]), warmup=0)
     assert step.graph is not None, step.error
     assert step.launches_per_step > 100
     graphed = []
-    for lr in lrs[2:]:
+    frozen = None
+    for k in range(2, len(lrs)):
         for g in opt.param_groups:
-            g["lr"] = lr
-        graphed.append(step(x, y).item())
-    # trajectory positions: constructor ran steps 0,1 eagerly and step 2 during capture (capture launches nothing), so the
-    # first replay is step 2 of the trajectory
+            g["lr"] = lrs[k]
+        if lrs[k] == 0.0 and frozen is None:
+            torch.cuda.synchronize()
+            frozen = opt.flat_param.clone()
+        graphed.append(step(*data[k & 1]).item())    # fresh data copied into the static inputs every step
+    # lr = 0 staged for the last two replays (pinned buffer → memcpy node): p -= lr * buf must not move anything
+    assert torch.equal(opt.flat_param, frozen), "the staged learning rate did not reach the captured SGD kernel"
     for k, (a, b) in enumerate(zip(eager[2:], graphed)):
         assert abs(a - b) < 2e-2 * abs(a), (k, eager, graphed)
-    # lr = 0 in the last two steps: parameters frozen → identical loss twice (proves the staged lr reached the kernel)
+    # the two batches give clearly different losses: a graph that kept a stale packed image would not follow `eager`
+    assert abs(eager[2] - eager[3]) > 1e-3 * abs(eager[2])
     # (p -= lr * momentum_buffer: with lr = 0 nothing moves; a stale capture-time lr of 1e-2 would change the loss)
-    assert abs(graphed[-1] - graphed[-2]) < 1e-4 * abs(graphed[-1]), graphed
+    # (steps 4 and 5 use different batches, so compare each with its eager twin instead of with each other)
+    assert abs(graphed[-1] - eager[-1]) < 2e-2 * abs(eager[-1]) and abs(graphed[-2] - eager[-2]) < 2e-2 * abs(eager[-2])
+    # and an eager step right after the replays must see the CURRENT weights (no stale bf16 packs): with lr = 0 the
+    # parameters are frozen, so it reproduces the last loss on the same batch
+    for g in opt.param_groups:
+        g["lr"] = 0.0
+    opt.zero_grad()
+    l_after = model(*data[1])
+    l_after.backward()
+    opt.step()
+    assert abs(l_after.item() - graphed[-1]) < 1e-3 * abs(graphed[-1]), (l_after.item(), graphed[-1])
     for p in model.parameters():
         assert torch.isfinite(p).all()

@@ -14,7 +14,7 @@ import torch
 
 
 class GraphedTrainStep(object):
-    def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True):
+    def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True, side_stream_warmup=False):
         self.model = model
         self.opt = optimizer
         self.static_inputs = [t.clone() for t in example_inputs]
@@ -27,12 +27,16 @@ class GraphedTrainStep(object):
             return
         from .. import _lib
         try:
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for _ in range(warmup):          # allocator pools, lazy attributes, FlatPack mirror all warm
+            if side_stream_warmup:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(warmup):
+                        self._eager(*self.static_inputs)
+                torch.cuda.current_stream(dev).wait_stream(side)
+            else:
+                for _ in range(warmup):          # lazy attributes, FlatPack mirror, per-thread context binding all warm
                     self._eager(*self.static_inputs)
-            torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
@@ -60,4 +64,12 @@ class GraphedTrainStep(object):
                 dst.copy_(src, non_blocking=True)
         self.opt.stage_hyperparams()
         self.graph.replay()
+        # Python-side caches describe the weights BEFORE the replayed SGD update: drop them so that an eager step (or
+        # evaluation) after a replay re-packs from the current parameters
+        from .. import ops
+        ops.pack_cache.cache.clear()
+        ops.pack_cache.step += 1
+        pack = getattr(self.opt, "pack", None)
+        if pack is not None:
+            pack.mark_fresh()
         return self.static_loss

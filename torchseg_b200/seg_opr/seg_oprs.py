@@ -22,7 +22,9 @@ _s2d_cache = {}
 
 def _packed_image(img):
     """space-to-depth pack of the fp32 NCHW input image, shared by the two 7x7 stems of BiSeNet"""
-    key = (img.data_ptr(), img._version, tuple(img.shape))
+    # valid within ONE optimiser step only (pack_cache.step advances at every optimizer.step()): a whole-step CUDA graph
+    # must contain the pack kernel, and a static input buffer refilled in place keeps its data_ptr
+    key = (img.data_ptr(), img._version, tuple(img.shape), ops.pack_cache.step)
     hit = _s2d_cache.get("k")
     if hit is not None and hit[0] == key:
         return hit[1]
