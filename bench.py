@@ -254,7 +254,8 @@ def main():
                     help="bisenet = BASELINE configs[1] (the metric); pspnet / dfn = secondary lines (SURVEY C3 / C4)")
     ap.add_argument("--size", type=int, default=0, help="input size override (pspnet default 480, the reference shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--graph", action="store_true",
+                    help="experimental: time the step as ONE CUDA graph replay (engine.graph.GraphedTrainStep); default = eager launches")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -326,7 +327,7 @@ def main():
     # stack — tools/diag_graph2.py)
     gstep = None
     ms = None
-    if world == 1 and not args.no_graph:
+    if world == 1 and args.graph:
         from torchseg_b200.engine.graph import GraphedTrainStep
         set_lr(it)
         gstep = GraphedTrainStep(model, opt, dev_batch, warmup=2)

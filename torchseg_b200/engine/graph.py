@@ -9,12 +9,20 @@ Usage:
     for it, batch in enumerate(loader):
         set the learning rates in optimizer.param_groups as usual
         loss = step(batch['data'], batch['label'])                # device tensors; copied into the static inputs
-If capture is impossible (non-CUDA device, an op that cannot be captured) the object silently runs eager steps."""
+If capture is impossible (non-CUDA device, an op that cannot be captured) the object runs eager steps and keeps the
+reason in `.error`.
+
+Status: EXPERIMENTAL. Verified on B200: capture + replay follow the eager trajectory (tests/test_gpu_bisenet.py::
+test_graphed_train_step_matches_eager; tools/diag_graph*.py at the bench size: 329 launches per graph), but in the full
+bench.py flow the capture was intermittently invalidated (cudaErrorStreamCaptureInvalidated) by a call not yet
+identified, and a failed capture leaves the eager step ~50 % slower — so bench.py keeps eager launches by default
+(`--graph` opts in)."""
 import torch
 
 
 class GraphedTrainStep(object):
-    def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True, side_stream_warmup=False):
+    def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True, side_stream_warmup=False,
+                 capture_error_mode="global"):
         self.model = model
         self.opt = optimizer
         self.static_inputs = [t.clone() for t in example_inputs]
@@ -40,7 +48,7 @@ class GraphedTrainStep(object):
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode=capture_error_mode):
                 self.static_loss = self._eager(*self.static_inputs)
             self.launches_per_step = _lib.launch_count() - n0
             self.graph = g
