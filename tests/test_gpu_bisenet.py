@@ -441,3 +441,42 @@ def test_graphed_train_step_matches_eager(cuda):
     assert abs(l_after.item() - graphed[-1]) < 1e-3 * abs(graphed[-1]), (l_after.item(), graphed[-1])
     for p in model.parameters():
         assert torch.isfinite(p).all()
+
+
+def test_bisenet_eval_forward_matches_oracle(cuda):
+    """inference branch of BiSeNet.forward (network.py:110-111): eval-mode BN from the running statistics (scale / shift
+    through tsb_bn_finalize with count 1), main head only, x8 bilinear, log_softmax — vs the oracle in eval mode"""
+    import torchseg_b200
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.utils.init_func import init_weight
+    from oracle import torch_ref as tr
+    torch.manual_seed(11)
+    model = BiSeNet(19, False, None, None, BN)
+    init_weight(model.business_layer, torch.nn.init.kaiming_normal_, BN, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():   # non-trivial running statistics and affine parameters
+        for m in model.modules():
+            if isinstance(m, BN):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 1.5 + 0.5)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x = torch.randn(2, 3, 128, 160, generator=g)
+    tr.set_bf16_emulation(True)
+    try:
+        with torch.no_grad():
+            lo, _ = tr.bisenet_r18_forward(x, sd, training=False)
+            ref = F.log_softmax(F.interpolate(lo[2], scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+    finally:
+        tr.set_bf16_emulation(False)
+    model.to(cuda)
+    torchseg_b200.prepare_model(model)
+    model.eval()
+    rm_before = model.context_path.bn1.running_mean.clone()
+    with torch.no_grad():
+        out = model(x.to(cuda))
+    assert tuple(out.shape) == (2, 19, 128, 160) and out.dtype == torch.float32
+    assert norm_err(out, ref) < 2e-2, norm_err(out, ref)
+    assert (out.argmax(1).cpu() == ref.argmax(1)).float().mean() > 0.97
+    assert torch.equal(model.context_path.bn1.running_mean, rm_before), "eval must not touch the running statistics"
