@@ -235,7 +235,7 @@ def run_reference_arm(args):
     line = dict(impl="reference", metric=METRIC, value=ips, unit="images/sec", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000.0 * n / ips, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic",
-                config=dict(workload="BiSeNet-R18 train step 1024x1024 19-class OHEM", batch_per_step=n, device="host CPU"),
+                config=dict(workload=WORKLOAD, batch_per_step=n, device="host CPU (bounded sample of the same workload)"),
                 cpu_baseline=dict(value=ips, unit="images/sec", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=ips, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
