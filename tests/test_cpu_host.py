@@ -185,3 +185,74 @@ def test_ddp_and_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=30)
     assert all(r[1] == "ok" for r in res), res
+
+
+def test_grad_share_protocol():
+    """ops.GradShare: first contributor's gradient is stashed (autograd gets None), the last one returns the shared
+    buffer; a late contributor that could not accumulate in place is added explicitly; the object re-arms"""
+    from torchseg_b200 import ops
+    g = ops.GradShare(2)
+    a = torch.ones(3)
+    assert g.contribute(a) is None and g.stash is a
+    a.add_(2.0)                                  # what the second consumer's dgrad epilogue does in place
+    out = g.contribute(a, accumulated=True)
+    assert out is a and float(out.sum()) == 9.0
+    assert g.stash is None and g.left == 2       # re-armed
+    # three contributors, the last one not in place
+    g3 = ops.GradShare(3)
+    b = torch.full((2,), 1.0)
+    assert g3.contribute(b) is None
+    assert g3.contribute(b, accumulated=True) is None
+    out = g3.contribute(torch.full((2,), 5.0))
+    assert torch.equal(out, torch.full((2,), 6.0))
+
+
+def test_ragged_channel_padding_is_differentiable():
+    """seg_oprs._pad_weight / _pad_vec (DFN's 21 / 171 / 9-channel layers): zero extension in KRSC layout whose autograd
+    slices the gradient back to the reference-shaped parameter"""
+    from torchseg_b200.seg_opr import seg_oprs as so
+    w = torch.randn(21, 9, 3, 3).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)   # KRSC-backed
+    wp = so._pad_weight(w, 64, 64)
+    assert tuple(wp.shape) == (64, 64, 3, 3) and wp.permute(0, 2, 3, 1).is_contiguous()
+    assert torch.equal(wp[:21, :9], w) and float(wp[21:].abs().sum()) == 0 and float(wp[:, 9:].abs().sum()) == 0
+    gfull = torch.randn(64, 64, 3, 3)
+    wp.backward(gfull)
+    assert torch.equal(w.grad, gfull[:21, :9])
+    v = torch.randn(21, requires_grad=True)
+    vp = so._pad_vec(v, 64, 1.0)
+    assert float(vp[21:].min()) == 1.0
+    vp.sum().backward()
+    assert torch.equal(v.grad, torch.ones(21))
+    assert so._ceil_to(171, 64) == 192 and so._ceil_to(64, 64) == 64
+
+
+def test_flat_pack_descriptor_table_and_staleness():
+    """optim.FlatPack: one 32-byte descriptor per eligible conv weight (offset, K, R*S, C, 32x32 tile counts), block
+    prefix sums, and the freshness protocol (stale before the first step / after an in-place weight edit)"""
+    import struct
+    from torchseg_b200 import optim, prepare_model
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(16, 40, 3, bias=False), torch.nn.BatchNorm2d(40),
+                              torch.nn.Conv2d(40, 24, 1, bias=True), torch.nn.Conv2d(3, 8, 3, bias=False))
+    prepare_model(net)
+    opt = optim.SGD(list(net.parameters()), lr=0.1, momentum=0.9)
+    fp = opt.pack
+    assert all(p._tsb_pack[0] is fp for p in net.parameters())
+    # eligible: K % 8 == 0 and C % 8 == 0 → the 16->40 3x3 and the 40->24 1x1; the 3-channel conv is not
+    assert fp.ntensors == 2
+    raw = bytes(fp.desc.numpy().tobytes())
+    d0 = struct.unpack("<qiiiiii", raw[:32])
+    d1 = struct.unpack("<qiiiiii", raw[32:64])
+    assert d0[1:6] == (40, 9, 16, 2, 1) and d1[1:6] == (24, 1, 40, 1, 2)
+    assert d0[0] == opt._spans[0][0] and d1[0] == opt._spans[3][0] and d0[0] % 8 == 0 and d1[0] % 8 == 0
+    assert fp.bstart.tolist() == [0, 9 * 2 * 1] and fp.nblocks == 18 + 2
+    w = net[0].weight
+    assert fp.lookup(w, w._tsb_pack[1], False) is None          # no optimiser step yet → per-tensor pack path
+    fp.mark_fresh()
+    hit = fp.lookup(w, w._tsb_pack[1], False)
+    assert hit is not None and tuple(hit[0].shape) == (40, 3, 3, 16) and hit[1] is None
+    with torch.no_grad():
+        w.mul_(2.0)                                              # in-place edit bumps the version → stale again
+    assert fp.lookup(w, w._tsb_pack[1], False) is None
+    opt.stage_hyperparams()
+    assert abs(float(opt._hp_host[0]) - 0.1) < 1e-7
