@@ -245,3 +245,38 @@ def test_module_key_names_match_reference():
     assert list(ref.keys()) == list(ours.keys())
     for k in ref:
         assert ref[k].shape == ours[k].shape, k
+
+
+def test_metric_functions_vs_live_reference():
+    """seg_opr.metric (confusion matrix / IoU / ADE intersection-union) against the reference's metric.py on seeded
+    predictions, incl. ignore labels (255 → outside [0, n_cl), -1 for ADE) and classes that never occur"""
+    import importlib.util
+    from torchseg_b200.seg_opr import metric as mine
+    rl = _live()
+    spec = importlib.util.spec_from_file_location("ref_metric", os.path.join(rl.REF, "furnace", "seg_opr", "metric.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(5)
+    n_cl = 19
+    gt = rng.integers(0, 17, size=(3, 64, 80))          # classes 17, 18 never occur → NaN IoU, skipped by nanmean
+    gt[:, :5] = 255
+    pred = np.where(rng.random(gt.shape) < 0.7, np.clip(gt, 0, 16), rng.integers(0, 17, size=gt.shape))
+    h1, l1, c1 = mine.hist_info(n_cl, pred, gt)
+    h2, l2, c2 = ref.hist_info(n_cl, pred, gt)
+    assert np.array_equal(h1, h2) and l1 == l2 and c1 == c2
+    for a, b in zip(mine.compute_score(h1, c1, l1), ref.compute_score(h2, c2, l2)):
+        assert np.allclose(a, b, equal_nan=True)
+    ht, lt, ct = mine.hist_info_torch(n_cl, torch.from_numpy(pred), torch.from_numpy(gt))
+    assert np.array_equal(ht.numpy(), h2) and int(lt) == l2 and int(ct) == c2
+    # ADE protocol
+    lab = rng.integers(-1, 150, size=(48, 64))
+    pr = np.where(rng.random(lab.shape) < 0.6, np.clip(lab, 0, 149), rng.integers(0, 150, size=lab.shape))
+    i1, u1 = mine.intersectionAndUnion(pr, lab, 150)
+    i2, u2 = ref.intersectionAndUnion(pr, lab, 150)
+    assert np.array_equal(i1, i2) and np.array_equal(u1, u2)
+    for a, b in zip(mine.meanIoU(np.stack([i1, i1], 1), np.stack([u1, u1], 1)), ref.meanIoU(np.stack([i2, i2], 1), np.stack([u2, u2], 1))):
+        assert np.allclose(a, b, equal_nan=True)
+    for a, b in zip(mine.pixelAccuracy(pr, lab), ref.pixelAccuracy(pr, lab)):
+        assert a == b
+    assert mine.mean_pixel_accuracy([3, 4], [5, 6]) == ref.mean_pixel_accuracy([3, 4], [5, 6])
+    assert mine.accuracy(pr, lab)[0] == ref.accuracy(pr, lab)[0]
