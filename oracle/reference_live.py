@@ -77,3 +77,14 @@ def load_network(rel_dir, num_classes=19, bn_eps=1e-5, bn_momentum=0.1, **extra)
         else:
             del sys.modules["config"]
     return mod
+
+
+def load_evaluator():
+    """reference engine.evaluator, importable under Python >= 3.10 with one more in-memory shim: img_utils.py:9 uses
+    `collections.Iterable` (removed in 3.10) → alias it to collections.abc.Iterable for the import"""
+    import collections
+    import collections.abc
+    _ensure_base()
+    if not hasattr(collections, "Iterable"):
+        collections.Iterable = collections.abc.Iterable
+    return importlib.import_module("engine.evaluator")

@@ -280,3 +280,71 @@ def test_metric_functions_vs_live_reference():
         assert a == b
     assert mine.mean_pixel_accuracy([3, 4], [5, 6]) == ref.mean_pixel_accuracy([3, 4], [5, 6])
     assert mine.accuracy(pr, lab)[0] == ref.accuracy(pr, lab)[0]
+
+
+def test_evaluator_sliding_and_whole_eval_vs_live_reference(monkeypatch):
+    """engine.evaluator (batched sliding-window evaluation) against the reference Evaluator run on the CPU with a small
+    deterministic network: same window grid, same summed (not averaged) overlap handling, same flip / multi-scale
+    accumulation, same cv2 resizes → identical arg-max maps and matching scores"""
+    rl = _live()
+    ref_mod = rl.load_evaluator()
+    from torchseg_b200.engine.evaluator import Evaluator
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self, raising=False)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.c1 = torch.nn.Conv2d(3, 8, 3, padding=1)
+            self.c2 = torch.nn.Conv2d(8, 5, 3, padding=2, dilation=2)
+
+        def forward(self, x):
+            return torch.log_softmax(self.c2(torch.relu(self.c1(x))) * 3.0, dim=1)
+
+    class RefWrap(object):       # the reference calls .eval() / .to(get_device()) (-1 on the CPU) on its val_func
+        def __init__(self, m):
+            self.m = m
+
+        def eval(self):
+            self.m.eval()
+
+        def to(self, *a):
+            return self
+
+        def __call__(self, x):
+            return self.m(x)
+
+    net = Net().double().float()
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(150, 210, 3), dtype=np.uint8)
+    kw = dict(dataset=None, class_num=5, image_mean=mean, image_std=std, network=None, multi_scales=[0.75, 1.0, 1.5],
+              is_flip=True, devices=[0])
+    mine = Evaluator(crop_batch=3, **kw)
+    mine.val_func = net
+
+    class _DS(object):
+        def get_length(self):
+            return 0
+    kw_ref = dict(kw, dataset=_DS())
+    ref = ref_mod.Evaluator(**kw_ref)
+    ref.val_func = RefWrap(net)
+    # sliding evaluation: crop 96 on a 150x210 image → 2x3 .. 3x5 windows per scale, incl. the single-window scale path
+    p_ref = ref.sliding_eval(img, 96, 2 / 3.0, None)
+    p_mine = mine.sliding_eval(img, 96, 2 / 3.0, None)
+    assert p_ref.shape == p_mine.shape == (150, 210)
+    assert (p_ref == p_mine).mean() > 0.999
+    s_ref = ref.scale_process(img, (150, 210), 96, 2 / 3.0, None)
+    s_mine = mine.scale_process(img, (150, 210), 96, 2 / 3.0, None)
+    assert np.abs(s_ref - s_mine).max() < 1e-4 * np.abs(s_ref).max()
+    assert mine.window_grid(150, 210, 96, 2 / 3.0) == [(0, 0), (0, 64), (0, 114), (54, 0), (54, 64), (54, 114)]
+    # small image → single padded window
+    small = img[:80, :70]
+    assert np.array_equal(ref.sliding_eval(small, 96, 2 / 3.0, None), mine.sliding_eval(small, 96, 2 / 3.0, None))
+    # whole-image evaluation with padding to a fixed input size and resize to an output size
+    w_ref = ref.whole_eval(img, (75, 105), (160, 224), None)
+    w_mine = mine.whole_eval(img, (75, 105), (160, 224), None)
+    assert (w_ref == w_mine).mean() > 0.999
+    # grey-scale input path
+    g = img[:, :, :1]
+    assert (ref.whole_eval(g, None, None, None) == mine.whole_eval(g, None, None, None)).mean() > 0.999

@@ -31,6 +31,6 @@ def install_as_furnace():
     import importlib
     import sys
     for name in ("seg_opr", "seg_opr.seg_oprs", "seg_opr.loss_opr", "seg_opr.metric", "base_model", "base_model.resnet", "engine",
-                 "engine.engine", "engine.lr_policy", "engine.logger", "utils", "utils.init_func", "utils.pyt_utils",
+                 "engine.engine", "engine.lr_policy", "engine.logger", "engine.evaluator", "utils", "utils.init_func", "utils.pyt_utils", "utils.img_utils",
                  "apex", "apex.parallel"):
         sys.modules[name] = importlib.import_module("torchseg_b200." + name)
