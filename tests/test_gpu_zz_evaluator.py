@@ -1,0 +1,63 @@
+"""Evaluator (engine/evaluator.py) driving the libtsb eval-mode BiSeNet forward on the GPU: multi-scale + flip sliding
+evaluation with batched windows, against the same evaluator driving the oracle network on the CPU.
+
+Written after the round's GPU budget was spent: the pieces are validated separately (eval forward on the GPU:
+test_bisenet_eval_forward_matches_oracle; evaluator logic pixel-for-pixel vs the live reference on the CPU), this
+composition has not run on hardware yet — hence the non-strict xfail marker, to be removed after its first green run."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BN = torch.nn.BatchNorm2d
+
+
+@pytest.mark.xfail(reason="composition not yet run on hardware (see module docstring)", strict=False)
+def test_sliding_eval_on_libtsb_bisenet(cuda):
+    import torchseg_b200
+    from torchseg_b200.engine.evaluator import Evaluator
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.utils.init_func import init_weight
+    from oracle import torch_ref as tr
+    torch.manual_seed(21)
+    model = BiSeNet(19, False, None, None, BN)
+    init_weight(model.business_layer, torch.nn.init.kaiming_normal_, BN, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+    g = torch.Generator().manual_seed(22)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, BN):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 1.5 + 0.5)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    class OracleNet(object):     # the oracle's eval forward behind the val_func protocol (eval / to / __call__)
+        def eval(self):
+            return self
+
+        def to(self, *a):
+            return self
+
+        def __call__(self, x):
+            tr.set_bf16_emulation(True)
+            try:
+                lo, _ = tr.bisenet_r18_forward(x, sd, training=False)
+                return F.log_softmax(F.interpolate(lo[2], scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+            finally:
+                tr.set_bf16_emulation(False)
+
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    rng = np.random.default_rng(23)
+    img = rng.integers(0, 256, size=(200, 300, 3), dtype=np.uint8)
+    kw = dict(dataset=None, class_num=19, image_mean=mean, image_std=std, network=None, multi_scales=[0.75, 1.0],
+              is_flip=True, devices=[0])
+    ref = Evaluator(crop_batch=4, **kw)
+    ref.val_func = OracleNet()
+    p_ref = ref.sliding_eval(img, 128, 2 / 3.0, None)
+    model.to(cuda)
+    torchseg_b200.prepare_model(model)
+    dev = Evaluator(crop_batch=4, **kw)
+    dev.val_func = model
+    p_dev = dev.sliding_eval(img, 128, 2 / 3.0, cuda)
+    assert p_dev.shape == (200, 300)
+    assert (p_dev == p_ref).mean() > 0.97
