@@ -254,5 +254,5 @@ def test_flat_pack_descriptor_table_and_staleness():
     with torch.no_grad():
         w.mul_(2.0)                                              # in-place edit bumps the version → stale again
     assert fp.lookup(w, w._tsb_pack[1], False) is None
-    opt.stage_hyperparams()
-    assert abs(float(opt._hp_host[0]) - 0.1) < 1e-7
+    opt.push_hyperparams()
+    assert abs(float(opt._hp_dev[0]) - 0.1) < 1e-7 and float(opt._hp_dev[1]) == 0.0

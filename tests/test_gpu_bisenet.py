@@ -366,7 +366,7 @@ def test_flat_bf16_mirror_matches_per_tensor_pack(cuda):
 def test_graphed_train_step_matches_eager(cuda):
     """GraphedTrainStep (whole step as one CUDA graph: zero_grad → forward → backward → fused SGD) follows the eager
     trajectory: same losses step by step (up to the non-deterministic summation order of the atomics), LR changes
-    between replays are honoured (pinned staging buffer → memcpy node)"""
+    between replays are honoured (push_hyperparams → the device tensor the captured kernel reads)"""
     import os
     if os.environ.get("TSB_TEST_GRAPH", "0") != "1":
         # engine/graph.py is EXPERIMENTAL: on this stack the capture is intermittently invalidated, and a failed capture
@@ -421,7 +421,7 @@ def test_graphed_train_step_matches_eager(cuda):
             torch.cuda.synchronize()
             frozen = opt.flat_param.clone()
         graphed.append(step(*data[k & 1]).item())    # fresh data copied into the static inputs every step
-    # lr = 0 staged for the last two replays (pinned buffer → memcpy node): p -= lr * buf must not move anything
+    # lr = 0 pushed for the last two replays (device tensor read by the captured SGD kernel): nothing may move
     assert torch.equal(opt.flat_param, frozen), "the staged learning rate did not reach the captured SGD kernel"
     for k, (a, b) in enumerate(zip(eager[2:], graphed)):
         assert abs(a - b) < 2e-2 * abs(a), (k, eager, graphed)

@@ -15,8 +15,12 @@ reason in `.error`.
 Status: EXPERIMENTAL. Verified on B200: capture + replay follow the eager trajectory (tests/test_gpu_bisenet.py::
 test_graphed_train_step_matches_eager; tools/diag_graph*.py at the bench size: 329 launches per graph), but in the full
 bench.py flow the capture was intermittently invalidated (cudaErrorStreamCaptureInvalidated) by a call not yet
-identified, and a failed capture leaves the eager step ~50 % slower — so bench.py keeps eager launches by default
-(`--graph` opts in)."""
+identified, and a failed capture leaves the eager step ~50 % slower and the process-wide CUDA RNG in capture mode — so
+bench.py keeps eager launches by default (`--graph` opts in) and the GPU test only runs with TSB_TEST_GRAPH=1.
+Two suspects were removed after the round's GPU budget was spent (not yet re-run on hardware): the cyclic GC is now
+collected before and disabled during the capture (torch.cuda.graph stopped doing that on entry), and the captured step
+no longer contains a pinned-host → device copy (hyper-parameters live in a device tensor refreshed by an eager copy
+before each replay)."""
 import torch
 
 
@@ -46,10 +50,22 @@ class GraphedTrainStep(object):
                 for _ in range(warmup):          # lazy attributes, FlatPack mirror, per-thread context binding all warm
                     self._eager(*self.static_inputs)
             torch.cuda.synchronize(dev)
+            import gc
+            self.opt.push_hyperparams()
+            torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g, capture_error_mode=capture_error_mode):
-                self.static_loss = self._eager(*self.static_inputs)
+            # torch.cuda.graph no longer garbage-collects on entry: collect now and keep the cyclic GC off while capturing,
+            # so that no CUDA object (tensor of an old autograd graph, stream, event) is destroyed in the middle of it
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode=capture_error_mode):
+                    self.static_loss = self._eager(*self.static_inputs)
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self.launches_per_step = _lib.launch_count() - n0
             self.graph = g
         except Exception as e:  # noqa: BLE001 — fall back to eager steps, keep the reason
@@ -70,7 +86,7 @@ class GraphedTrainStep(object):
         for dst, src in zip(self.static_inputs, inputs):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        self.opt.stage_hyperparams()
+        self.opt.push_hyperparams()      # lr / weight decay of this step → the device tensor the captured SGD kernel reads
         self.graph.replay()
         # Python-side caches describe the weights BEFORE the replayed SGD update: drop them so that an eager step (or
         # evaluation) after a replay re-packs from the current parameters

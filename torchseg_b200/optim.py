@@ -97,13 +97,10 @@ class SGD(object):
         self._seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
         self._steps = 0
         self.grad_scale = 1.0
-        # per-group lr / weight-decay scalars read by the kernel from device memory. They are refreshed from a PINNED
-        # host buffer by an async copy inside step(): under CUDA-graph capture that copy becomes a memcpy node which
-        # re-reads the host buffer at every replay, so `stage_hyperparams()` is all a graphed train loop has to call.
+        # per-group lr / weight-decay scalars read by the kernel from device memory. Eager steps build them per call;
+        # a captured step (engine.graph.GraphedTrainStep) reads this persistent device tensor instead, which the
+        # graphed loop refreshes with `push_hyperparams()` (a small eager copy) before every replay.
         ng = len(self.param_groups)
-        self._hp_host = torch.zeros(2 * ng, dtype=torch.float32)
-        if dev.type == "cuda":
-            self._hp_host = self._hp_host.pin_memory()
         self._hp_dev = torch.zeros(2 * ng, dtype=torch.float32, device=dev)
 
     def zero_grad(self, set_to_none=False):
@@ -111,21 +108,17 @@ class SGD(object):
         self.flat_grad.zero_()
         ops.zero_arena.reset()
 
-    def stage_hyperparams(self):
-        """write the current param_groups lr / weight_decay into the pinned staging buffer"""
-        ng = len(self.param_groups)
-        for i, g in enumerate(self.param_groups):
-            self._hp_host[i] = float(g["lr"])
-            self._hp_host[ng + i] = float(g["weight_decay"])
+    def push_hyperparams(self):
+        """copy the current param_groups lr / weight_decay into the persistent device tensor (eager, outside any capture)"""
+        vals = [float(g["lr"]) for g in self.param_groups] + [float(g["weight_decay"]) for g in self.param_groups]
+        self._hp_dev.copy_(torch.tensor(vals, dtype=torch.float32))
 
     def step(self, closure=None):
         ensure_flat_grads(self._params)
         ng = len(self.param_groups)
         dev = self.flat_param.device
         if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
-            # graph capture: a memcpy node from the pinned staging buffer (re-read at every replay)
-            self.stage_hyperparams()
-            self._hp_dev.copy_(self._hp_host, non_blocking=True)
+            # graph capture: no host→device traffic inside the graph; the caller keeps _hp_dev current (push_hyperparams)
             lr, wd = self._hp_dev[:ng], self._hp_dev[ng:]
         else:
             # eager: a pageable H2D copy is staged at call time, so a CPU running ahead can never change the values of
