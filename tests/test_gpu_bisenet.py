@@ -387,6 +387,7 @@ def test_graphed_train_step_matches_eager(cuda):
         return model, optim.SGD(groups, lr=1e-2, momentum=0.9, weight_decay=5e-4), data
 
     lrs = [1e-2, 1e-2, 8e-3, 6e-3, 0.0, 0.0]
+    batch_of = lambda k: 0 if k < 2 else (k & 1)     # steps 0, 1 = the constructor's warm-up on its static inputs
     # eager reference trajectory
     model, opt, data = make()
     eager = []
@@ -394,22 +395,17 @@ def test_graphed_train_step_matches_eager(cuda):
         for g in opt.param_groups:
             g["lr"] = lr
         opt.zero_grad()
-        loss = model(*data[k & 1])
+        loss = model(*data[batch_of(k)])
         loss.backward()
         opt.step()
         eager.append(loss.item())
-    # graphed: the constructor runs two eager warm-up steps on its static inputs (= trajectory steps 0 and 1 must see
-    # batches 0 and 1, so warm up by hand and capture with warmup=0)
+    # graphed: the constructor runs trajectory steps 0 and 1 eagerly on a SIDE stream (PyTorch's capture requirement),
+    # then captures; every later step is a replay fed with fresh data
     model, opt, data = make()
-    for k in (0, 1):
-        for g in opt.param_groups:
-            g["lr"] = lrs[k]
-        opt.zero_grad()
-        loss = model(*data[k & 1])
-        loss.backward()
-        opt.step()
-    step = GraphedTrainStep(model, opt, list(data[0]), warmup=0)
-    if step.graph is None:   # experimental feature (engine/graph.py): capture is intermittently invalidated on this stack
+    for g in opt.param_groups:
+        g["lr"] = lrs[0]
+    step = GraphedTrainStep(model, opt, list(data[0]), warmup=2)
+    if step.graph is None:   # experimental feature (engine/graph.py)
         pytest.skip("CUDA graph capture unavailable: %s" % (step.error or "")[:200])
     assert step.launches_per_step > 100
     graphed = []
@@ -420,7 +416,7 @@ def test_graphed_train_step_matches_eager(cuda):
         if lrs[k] == 0.0 and frozen is None:
             torch.cuda.synchronize()
             frozen = opt.flat_param.clone()
-        graphed.append(step(*data[k & 1]).item())    # fresh data copied into the static inputs every step
+        graphed.append(step(*data[batch_of(k)]).item())    # fresh data copied into the static inputs every step
     # lr = 0 pushed for the last two replays (device tensor read by the captured SGD kernel): nothing may move
     assert torch.equal(opt.flat_param, frozen), "the staged learning rate did not reach the captured SGD kernel"
     for k, (a, b) in enumerate(zip(eager[2:], graphed)):
@@ -435,7 +431,7 @@ def test_graphed_train_step_matches_eager(cuda):
     for g in opt.param_groups:
         g["lr"] = 0.0
     opt.zero_grad()
-    l_after = model(*data[1])
+    l_after = model(*data[batch_of(len(lrs) - 1)])
     l_after.backward()
     opt.step()
     assert abs(l_after.item() - graphed[-1]) < 1e-3 * abs(graphed[-1]), (l_after.item(), graphed[-1])

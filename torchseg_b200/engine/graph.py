@@ -17,15 +17,19 @@ test_graphed_train_step_matches_eager; tools/diag_graph*.py at the bench size: 3
 bench.py flow the capture was intermittently invalidated (cudaErrorStreamCaptureInvalidated) by a call not yet
 identified, and a failed capture leaves the eager step ~50 % slower and the process-wide CUDA RNG in capture mode — so
 bench.py keeps eager launches by default (`--graph` opts in) and the GPU test only runs with TSB_TEST_GRAPH=1.
-Two suspects were removed after the round's GPU budget was spent (not yet re-run on hardware): the cyclic GC is now
-collected before and disabled during the capture (torch.cuda.graph stopped doing that on entry), and the captured step
-no longer contains a pinned-host → device copy (hyper-parameters live in a device tensor refreshed by an eager copy
-before each replay)."""
+What the B200 runs showed (tools/diag_graph*.py, tests): captures preceded by warm-up steps on a SIDE stream succeeded
+(first version of the test, diag_graph2 VAR b), captures preceded only by default-stream steps failed (bench flow, the
+test with a hand-written default-stream warm-up) — consistent with PyTorch's documented requirement that the warm-up
+run on a side stream (autograd's leaf-gradient streams must not be the legacy default stream, whose implicit use inside
+a global-mode capture invalidates it); the side-stream warm-up is therefore the default again, with `warmup >= 1`
+required. Ruled out on hardware: cyclic GC during capture (now collected before / disabled during the capture anyway)
+and the pinned-host → device hyper-parameter copy inside the graph (removed: hyper-parameters live in a device tensor
+refreshed by an eager copy before each replay)."""
 import torch
 
 
 class GraphedTrainStep(object):
-    def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True, side_stream_warmup=False,
+    def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True, side_stream_warmup=True,
                  capture_error_mode="global"):
         self.model = model
         self.opt = optimizer
@@ -37,6 +41,8 @@ class GraphedTrainStep(object):
         dev = self.static_inputs[0].device
         if not enable or dev.type != "cuda":
             return
+        if side_stream_warmup and warmup < 1:
+            warmup = 1       # at least one step must have run on a non-default stream before the capture
         from .. import _lib
         try:
             if side_stream_warmup:
