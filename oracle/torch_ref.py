@@ -314,6 +314,13 @@ def refine_residual(x, sd, prefix, has_relu, eps, momentum, training, stats=None
     return q(F.relu(t + x)) if has_relu else q(t + x)
 
 
+def bn_refine(x, sd, prefix, has_relu, eps, momentum, training, stats=None):
+    """BNRefine.forward — /root/reference/furnace/seg_opr/seg_oprs.py:157-162"""
+    t = conv_bn_relu(x, sd, prefix + ".conv_bn_relu", 1, 1, eps=eps, momentum=momentum, training=training, stats=stats)
+    t = q(F.conv2d(t, qw(sd[prefix + ".conv_refine.weight"]), None, 1, 1))
+    return q(F.relu(t + x)) if has_relu else q(t + x)
+
+
 def channel_attention(x1, x2, sd, prefix):
     """ChannelAttention.forward + SELayer.forward — seg_oprs.py:121-126,135-140"""
     fm = torch.cat([x1, x2], 1)
