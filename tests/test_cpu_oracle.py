@@ -348,3 +348,23 @@ def test_evaluator_sliding_and_whole_eval_vs_live_reference(monkeypatch):
     # grey-scale input path
     g = img[:, :, :1]
     assert (ref.whole_eval(g, None, None, None) == mine.whole_eval(g, None, None, None)).mean() > 0.999
+
+
+def test_oracle_dfn_blocks_vs_live_reference_modules():
+    """RefineResidual / BNRefine / ChannelAttention restatements against the live reference modules (bit-exact, fp32)"""
+    from oracle import torch_ref as tr
+    rl = _live()
+    so = rl.load_seg_oprs()
+    torch.manual_seed(3)
+    x = torch.randn(2, 16, 9, 11)
+    for relu in (True, False):
+        m = so.BNRefine(16, 16, 3, has_relu=relu).train()
+        sd = {"m." + k: v.detach().clone() for k, v in m.state_dict().items()}
+        assert torch.equal(tr.bn_refine(x, sd, "m", relu, 1e-5, 0.1, True), m(x))
+        m = so.RefineResidual(16, 24, 3, has_relu=relu).train()
+        sd = {"m." + k: v.detach().clone() for k, v in m.state_dict().items()}
+        assert torch.equal(tr.refine_residual(x, sd, "m", relu, 1e-5, 0.1, True), m(x))
+    m = so.ChannelAttention(32, 16, 1)
+    sd = {"m." + k: v.detach().clone() for k, v in m.state_dict().items()}
+    x2 = torch.randn(2, 16, 9, 11)
+    assert torch.allclose(tr.channel_attention(x, x2, sd, "m"), m(x, x2), atol=1e-6)
