@@ -77,7 +77,14 @@ class GraphedTrainStep(object):
         except Exception as e:  # noqa: BLE001 — fall back to eager steps, keep the reason
             self.error = "%s: %s" % (type(e).__name__, e)
             self.graph = None
-            torch.cuda.synchronize(dev)
+            try:                 # best effort: release the half-built graph (its RNG registration, its memory pool)
+                g.reset()
+            except Exception:    # noqa: BLE001
+                pass
+            try:
+                torch.cuda.synchronize(dev)
+            except Exception:    # noqa: BLE001
+                pass
 
     def _eager(self, *inputs):
         self.opt.zero_grad()
