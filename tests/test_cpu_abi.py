@@ -69,3 +69,20 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
         _lib.lib()
+
+
+def test_product_package_never_imports_oracle():
+    """DESIGN.md §1 'No fallback': nothing under torchseg_b200/ (nor bench.py's product arm helpers) may import, call or
+    load anything under oracle/ — the oracle is test infrastructure only"""
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b|from\s+\.+oracle\b)|libtsb_oracle|oracle[/\\.]_ref", re.M)
+    bad = []
+    pkg = os.path.join(ROOT, "torchseg_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                if pat.search(src):
+                    bad.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert not bad, "product files reference the oracle: %s" % bad
+    hdr = open(os.path.join(ROOT, "include", "tsb.h")).read()
+    assert "oracle" not in hdr.lower()

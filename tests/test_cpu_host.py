@@ -256,3 +256,114 @@ def test_flat_pack_descriptor_table_and_staleness():
     assert fp.lookup(w, w._tsb_pack[1], False) is None
     opt.push_hyperparams()
     assert abs(float(opt._hp_dev[0]) - 0.1) < 1e-7 and float(opt._hp_dev[1]) == 0.0
+
+
+def test_flat_grad_layout_ownership():
+    """two owners over different parameter lists must not silently re-point .grad (the first owner would keep
+    stepping on a stale buffer of zeros): same set → DDP re-uses the optimiser's layout; a new optimiser takes over and
+    the OLD owner then fails loudly; anything else is refused."""
+    from torchseg_b200 import flat
+    a = [nn.Parameter(torch.randn(4, 3)), nn.Parameter(torch.randn(5))]
+    b = [nn.Parameter(torch.randn(2, 2))]
+    fa, spans_a = flat.ensure_flat_grads(a, take_over=True)
+    assert flat.ensure_flat_grads(a)[0] is fa                      # idempotent
+    lay = flat.layout_of(list(reversed(a)))                        # same SET, any order → the registered layout
+    assert lay is not None and lay[0] is fa and lay[2][0] is a[0]
+    with pytest.raises(RuntimeError, match="layout conflict"):     # overlapping, different list, no take-over
+        flat.ensure_flat_grads(a + b)
+    assert a[0].grad.data_ptr() == fa.data_ptr()                   # ... and nothing was re-pointed
+    fab, _ = flat.ensure_flat_grads(a + b, take_over=True)         # a new optimiser takes the parameters over
+    assert a[0].grad.data_ptr() == fab.data_ptr()
+    with pytest.raises(RuntimeError, match="layout conflict"):     # the old owner's zero_grad()/step() now raises
+        flat.ensure_flat_grads(a)
+    a[0].grad = None                                               # set_to_none upstream: the view is re-established
+    flat.ensure_flat_grads(a + b)
+    assert a[0].grad.data_ptr() == fab.data_ptr()
+    with pytest.raises(RuntimeError):
+        flat.check_inside(a, fa, spans_a)
+    flat.release(a + b)
+
+
+def test_fused_sgd_state_dict_is_torch_format():
+    """engine.py:103,142-146 store optimizer.state_dict(): the fused SGD reads and writes torch.optim.SGD's format"""
+    from torchseg_b200 import optim, flat
+    torch.manual_seed(0)
+    conv = nn.Conv2d(8, 16, 3, bias=True)
+    import torchseg_b200
+    torchseg_b200.prepare_model(conv)   # KRSC strides: momentum buffers must still come out as logical NCHW
+    bn = nn.BatchNorm2d(16)
+    groups = [dict(params=[conv.weight], lr=1e-2, weight_decay=5e-4),
+              dict(params=[conv.bias, bn.weight, bn.bias], lr=1e-1, weight_decay=0.0)]
+    ref = torch.optim.SGD([dict(g) for g in groups], lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    for p in ref.param_groups[0]["params"] + ref.param_groups[1]["params"]:
+        p.grad = torch.randn_like(p)
+    ref.step()
+    sd_ref = ref.state_dict()
+    for p in (conv.weight, conv.bias, bn.weight, bn.bias):
+        p.grad = None
+    opt = optim.SGD(groups, lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    assert opt.state_dict()["state"] == {}                      # fresh optimiser: no buffers, like torch
+    opt.load_state_dict(sd_ref)                                 # a reference / torch.optim.SGD checkpoint restores
+    assert opt._steps == 1
+    sd = opt.state_dict()
+    assert set(sd.keys()) == {"state", "param_groups"}
+    assert [g["params"] for g in sd["param_groups"]] == [g["params"] for g in sd_ref["param_groups"]]
+    for i, ent in sd_ref["state"].items():
+        got = sd["state"][i]["momentum_buffer"]
+        assert got.is_contiguous() and torch.equal(got, ent["momentum_buffer"])
+    for g, gr in zip(sd["param_groups"], sd_ref["param_groups"]):
+        for k in ("lr", "momentum", "weight_decay", "dampening", "nesterov"):
+            assert g[k] == gr[k], k
+    ref2 = torch.optim.SGD([dict(g) for g in groups], lr=1e-2, momentum=0.9, weight_decay=5e-4)
+    ref2.load_state_dict(sd)                                    # ... and the reference can resume from ours
+    assert torch.equal(ref2.state_dict()["state"][0]["momentum_buffer"], sd_ref["state"][0]["momentum_buffer"])
+    # round-1 native format still loads
+    opt.load_state_dict({"flat_momentum": opt.flat_mom.clone(), "steps": 3,
+                         "param_groups": [{"lr": 0.5}, {"lr": 0.25}]})
+    assert opt._steps == 3 and opt.param_groups[0]["lr"] == 0.5
+    flat.release(opt._params)
+
+
+def test_pack_cache_is_bounded_and_packed_image_matches_by_identity(monkeypatch):
+    """ADVICE r1: (a) one pack entry per (weight, kind) — a version bump overwrites, dead weights are swept;
+    (b) the space-to-depth image cache matches by tensor identity, not by address"""
+    from torchseg_b200 import ops
+    from torchseg_b200.seg_opr import seg_oprs
+    calls = []
+    monkeypatch.setattr(ops, "call", lambda name, *a: calls.append(name))
+    monkeypatch.setattr(ops, "ptr", lambda t: 0)
+    monkeypatch.setattr(ops, "stream", lambda: 0)
+    pc = ops._PackCache()
+    w = nn.Parameter(torch.randn(8, 8, 3, 3).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2))
+    pc.get(w, False)
+    pc.get(w, False)
+    assert calls.count("tsb_pack_weight") == 1 and len(pc.cache) == 1
+    pc.get(w, True)                                # now the transposed operand is needed too: re-pack, same entry
+    assert calls.count("tsb_pack_weight") == 2 and len(pc.cache) == 1
+    for _ in range(5):                             # torch.optim-style in-place updates bump the version
+        with torch.no_grad():
+            w.add_(1.0)
+        pc.get(w, True)
+    assert len(pc.cache) == 1 and calls.count("tsb_pack_weight") == 7
+    for _ in range(600):                           # per-forward temporaries (DFN's padded weights) are swept
+        t = torch.randn(8, 8, 1, 1).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        pc.get(t, False)
+        del t
+    assert len(pc.cache) < 520
+    # (b)
+    packs = []
+    monkeypatch.setattr(ops, "pack_image_s2d", lambda img: packs.append(img) or ("packed", len(packs)))
+    seg_oprs._release_packed_image()
+    img = torch.zeros(1, 3, 8, 8)
+    p1 = seg_oprs._packed_image(img)
+    assert seg_oprs._packed_image(img) is p1 and len(packs) == 1
+    twin = torch.as_strided(img, img.shape, img.stride())      # same storage/address, another tensor object
+    assert twin.data_ptr() == img.data_ptr()
+    assert seg_oprs._packed_image(twin) is not p1 and len(packs) == 2
+    img2 = torch.zeros(1, 3, 8, 8)
+    seg_oprs._packed_image(img2)
+    img2.add_(1.0)                                              # refilled in place → new version → re-pack
+    seg_oprs._packed_image(img2)
+    assert len(packs) == 4
+    seg_oprs._release_packed_image()
+    assert not seg_oprs._s2d_cache

@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from ... import ops
-from ...flat import ensure_flat_grads
+from ...flat import ensure_flat_grads, layout_of
 
 
 def _world():
@@ -38,11 +38,10 @@ class DistributedDataParallel(nn.Module):
         self.world_size = _world()
         self.bucket_bytes = bucket_bytes
         params = [p for p in module.parameters() if p.requires_grad]
-        reg = getattr(ensure_flat_grads, "_reg", None)
-        if reg is not None and set(reg[0]) == set(id(p) for p in params):
-            # the fused optimiser already laid the gradients out (group order): reuse that buffer/order
-            by_id = {id(p): p for p in params}
-            params = [by_id[i] for i in reg[0]]
+        lay = layout_of(params)
+        if lay is not None:
+            # the fused optimiser already laid these gradients out (group order): reuse that buffer/order
+            params = list(lay[2])
         self._params = params
         dev = params[0].device
         self.flat_grad, self._spans = ensure_flat_grads(params)
@@ -113,7 +112,7 @@ class DistributedDataParallel(nn.Module):
         self._pending = False
 
     def zero_grad(self, set_to_none=False):
-        ensure_flat_grads(self._params)
+        self.flat_grad, _ = ensure_flat_grads(self._params)
         self.flat_grad.zero_()
         ops.zero_arena.reset()
 

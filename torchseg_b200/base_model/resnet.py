@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..seg_opr.seg_oprs import conv_bn_act, _as_act
+from ..seg_opr.seg_oprs import conv_bn_act, _as_act, _release_packed_image
 from ..utils.pyt_utils import load_model
 
 __all__ = ['ResNet', 'resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152']
@@ -132,6 +132,7 @@ class ResNet(nn.Module):
 
     def forward_from_stem(self, x):
         """stages after conv1 → bn1 → relu (the stem may be computed elsewhere, fused with a sibling stem)"""
+        _release_packed_image()   # every stem of this forward has consumed the space-to-depth image by now
         x = ops.MaxPool3x3S2Fn.apply(x)
         blocks = []
         x = self.layer1(x)

@@ -82,14 +82,26 @@ def make_shape(N, H, W, C, K, R, stride, pad, dil):
 # bf16 weight packs, cached per optimiser step
 # --------------------------------------------------------------------------------------------------
 class _PackCache:
+    """bf16 operand packs of conv weights that are not served by the flat mirror (optim.FlatPack): weights before the
+    first fused optimiser step, torch.optim.* flows, padded / viewed weights, stems. At most ONE entry per
+    (weight object, operand kind); an entry is overwritten when the weight's version changes and dropped when the
+    weight is gone (DFN's per-forward padded temporaries), so the cache cannot grow with the step count."""
+
     def __init__(self):
         self.step = 0
         self.cache = {}
+        self._sweep_at = 256
 
     def invalidate(self):
         self.step += 1
         self.cache.clear()
         zero_arena.reset()
+
+    def _sweep(self):
+        dead = [k for k, v in self.cache.items() if v[2]() is None]
+        for k in dead:
+            del self.cache[k]
+        self._sweep_at = max(256, 2 * len(self.cache))
 
     def get(self, w, want_t, pad_k=None, stem=False):
         fp = getattr(w, "_tsb_pack", None)
@@ -97,15 +109,16 @@ class _PackCache:
             hit = fp[0].lookup(w, fp[1], want_t)   # bf16 mirror of the flat parameter buffer (optim.FlatPack)
             if hit is not None:
                 return hit
-        key = (id(w), w.data_ptr(), bool(want_t), pad_k, stem, w._version)
+        key = (id(w), pad_k, stem)
+        ver = (w.data_ptr(), w._version)
         hit = self.cache.get(key)
-        if hit is not None and hit[2]() is w:
+        if hit is not None and hit[2]() is w and hit[3] == ver and (hit[1] is not None or not want_t or stem):
             return hit[0], hit[1]
         K, C, R, S = w.shape
         if stem:
             wp = torch.empty((K, 4, 4, 16), dtype=_BF, device=w.device)
             call("tsb_pack_stem_weight", ptr(_krsc_ptr(w)), K, R, ptr(wp), stream())
-            out = (wp, None, weakref.ref(w))
+            out = (wp, None, weakref.ref(w), ver)
         else:
             src = _krsc_ptr(w)
             if pad_k is not None and pad_k != K:  # classifier: pad K (19) up to 64 rows of zeros
@@ -115,12 +128,28 @@ class _PackCache:
             wb = torch.empty((K, R, S, C), dtype=_BF, device=w.device)
             wt = torch.empty((C, R, S, K), dtype=_BF, device=w.device) if want_t else None
             call("tsb_pack_weight", ptr(src), K, R, S, C, ptr(wb), ptr(wt), stream())
-            out = (wb, wt, weakref.ref(w))
+            out = (wb, wt, weakref.ref(w), ver)
         self.cache[key] = out
+        if len(self.cache) > self._sweep_at:
+            self._sweep()
         return out[0], out[1]
 
 
 pack_cache = _PackCache()
+
+
+def _install_optimizer_hook():
+    """torch.optim.* flows (INTEGRATION.md keeps them supported): every optimiser step changes the weights, so the
+    per-tensor packs are dropped and the zero arena is recycled, exactly as the fused SGD does itself"""
+    try:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+    except ImportError:  # pragma: no cover
+        return
+
+    def _post(opt, args, kwargs):
+        pack_cache.invalidate()
+
+    register_optimizer_step_post_hook(_post)
 
 
 class _ZeroArena(object):
@@ -154,6 +183,7 @@ class _ZeroArena(object):
 
 
 zero_arena = _ZeroArena()
+_install_optimizer_hook()
 
 # set by the DDP shim: called with a parameter whose gradient has just been written DIRECTLY into its flat .grad view
 grad_ready_hook = None

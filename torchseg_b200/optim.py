@@ -5,7 +5,7 @@ import torch
 
 from . import ops
 from ._lib import call, ptr, stream
-from .flat import flatten, ensure_flat_grads
+from .flat import flatten, ensure_flat_grads, check_inside
 
 
 class FlatPack(object):
@@ -86,7 +86,7 @@ class SGD(object):
         self._params = [p for g in self.param_groups for p in g["params"]]
         assert len(set(id(p) for p in self._params)) == len(self._params), "a parameter appears in two groups"
         self.flat_param, self._spans = flatten(self._params, "data")
-        self.flat_grad, _ = ensure_flat_grads(self._params)
+        self.flat_grad, _ = ensure_flat_grads(self._params, take_over=True)
         self.flat_mom = torch.zeros_like(self.flat_param)
         self.pack = FlatPack(self._params, self._spans, self.flat_param.numel(), self.flat_param.device)
         ends, idx = [], 0
@@ -104,7 +104,7 @@ class SGD(object):
         self._hp_dev = torch.zeros(2 * ng, dtype=torch.float32, device=dev)
 
     def zero_grad(self, set_to_none=False):
-        ensure_flat_grads(self._params)
+        self.flat_grad, _ = ensure_flat_grads(self._params)   # raises if another owner took these gradients over
         self.flat_grad.zero_()
         ops.zero_arena.reset()
 
@@ -114,7 +114,8 @@ class SGD(object):
         self._hp_dev.copy_(torch.tensor(vals, dtype=torch.float32))
 
     def step(self, closure=None):
-        ensure_flat_grads(self._params)
+        self.flat_grad, _ = ensure_flat_grads(self._params)
+        check_inside(self._params, self.flat_grad, self._spans)
         ng = len(self.param_groups)
         dev = self.flat_param.device
         if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
@@ -127,17 +128,58 @@ class SGD(object):
             wd = torch.tensor([float(g["weight_decay"]) for g in self.param_groups], dtype=torch.float32, device=dev)
         call("tsb_sgd_flat_pack", ptr(self.flat_param), ptr(self.flat_grad), ptr(self.flat_mom), self.flat_param.numel(),
              ptr(self._seg_end), ptr(lr), ptr(wd), len(self.param_groups), float(self.momentum), float(self.grad_scale),
-             1 if self._steps == 0 else 0, ptr(self.pack.wb_flat), stream())
+             0, ptr(self.pack.wb_flat), stream())   # first_step = 0: the momentum buffer starts at exact zeros, and
+        # fma(momentum, 0, g) == g, so step 1 needs no special case (nothing step-dependent is baked into a captured graph)
         self._steps += 1
         ops.pack_cache.invalidate()  # per-tensor bf16 packs are stale now
         self.pack.mark_fresh()       # ... and the flat bf16 mirror written by the kernel above is current
 
+    # ---- checkpoint format: torch.optim.SGD's (what the reference stores under 'optimizer',
+    # /root/reference/furnace/engine/engine.py:103,142-146): {'state': {i: {'momentum_buffer': [K,C,R,S] fp32}},
+    # 'param_groups': [{'lr','momentum','dampening','weight_decay','nesterov',..., 'params': [indices]}]}
     def state_dict(self):
-        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
-        return {"flat_momentum": self.flat_mom.detach().cpu(), "steps": self._steps, "param_groups": groups}
+        groups, idx = [], 0
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d.setdefault("dampening", 0)
+            d.setdefault("nesterov", False)
+            d.setdefault("maximize", False)
+            d.setdefault("foreach", None)
+            d.setdefault("differentiable", False)
+            d.setdefault("fused", None)
+            d["params"] = list(range(idx, idx + len(g["params"])))
+            idx += len(g["params"])
+            groups.append(d)
+        state = {}
+        if self._steps > 0 and self.momentum != 0:
+            mom = self.flat_mom.detach().cpu()
+            for i, (p, (lo, hi)) in enumerate(zip(self._params, self._spans)):
+                # logical [K,C,R,S] view with the parameter's strides, made contiguous (NCHW) like torch's buffer
+                state[i] = {"momentum_buffer": torch.as_strided(mom, p.shape, p.stride(), lo).contiguous()}
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
-        self.flat_mom.copy_(sd["flat_momentum"])
-        self._steps = int(sd["steps"])
-        for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+        if "flat_momentum" in sd:          # round-1 native format
+            self.flat_mom.copy_(sd["flat_momentum"])
+            self._steps = int(sd["steps"])
+        else:
+            state = sd.get("state", {})
+            n_in = sum(len(g["params"]) for g in sd["param_groups"])
+            if n_in != len(self._params) or len(sd["param_groups"]) != len(self.param_groups):
+                raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+            self.flat_mom.zero_()
+            got = 0
+            order = [i for g in sd["param_groups"] for i in g["params"]]   # saved index of our k-th parameter
+            for k, (p, (lo, hi)) in enumerate(zip(self._params, self._spans)):
+                ent = state.get(order[k], state.get(str(order[k])))
+                buf = None if ent is None else ent.get("momentum_buffer")
+                if buf is None:
+                    continue
+                if tuple(buf.shape) != tuple(p.shape):
+                    raise ValueError("momentum_buffer %d has shape %s, parameter has %s" % (k, tuple(buf.shape), tuple(p.shape)))
+                torch.as_strided(self.flat_mom, p.shape, p.stride(), lo).copy_(buf)
+                got += 1
+            # torch creates a parameter's buffer at its first step with a gradient: any buffer present ⇒ not the first step
+            self._steps = 1 if got > 0 else 0
+        for g, s_ in zip(self.param_groups, sd["param_groups"]):
+            g.update({k: v for k, v in s_.items() if k != "params"})

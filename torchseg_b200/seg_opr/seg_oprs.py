@@ -21,16 +21,23 @@ _s2d_cache = {}
 
 
 def _packed_image(img):
-    """space-to-depth pack of the fp32 NCHW input image, shared by the two 7x7 stems of BiSeNet"""
-    # valid within ONE optimiser step only (pack_cache.step advances at every optimizer.step()): a whole-step CUDA graph
-    # must contain the pack kernel, and a static input buffer refilled in place keeps its data_ptr
-    key = (img.data_ptr(), img._version, tuple(img.shape), ops.pack_cache.step)
+    """space-to-depth pack of the fp32 NCHW input image, shared by the two 7x7 stems of BiSeNet.
+
+    The cache holds a STRONG reference to the image tensor and matches by identity (`is`) + version, never by address:
+    a fresh `imgs.cuda()` batch can be handed the freed storage of the previous one by the caching allocator, so a
+    data_ptr key would silently serve the previous batch's pack. `pack_cache.step` is part of the key because a
+    whole-step CUDA graph must contain the pack kernel even though the static input keeps identity and version between
+    the warm-up and the capture. Networks clear the cache at the end of their forward (`_release_packed_image`)."""
     hit = _s2d_cache.get("k")
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    if hit is not None and hit[0] is img and hit[1] == (img._version, ops.pack_cache.step):
+        return hit[2]
     packed = ops.pack_image_s2d(img.contiguous().float())
-    _s2d_cache["k"] = (key, packed)
+    _s2d_cache["k"] = (img, (img._version, ops.pack_cache.step), packed)
     return packed
+
+
+def _release_packed_image():
+    _s2d_cache.clear()
 
 
 def _ceil_to(n, m):
