@@ -228,6 +228,24 @@ def fcn_r18_loss(data, label, sd, aux_ratio=0.5, ignore_label=255, eps=1e-5, mom
     return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label)
 
 
+def fcn_r101_loss(data, label, sd, layers=(3, 4, 23, 3), aux_ratio=0.5, ignore_label=255, eps=1e-5, momentum=0.1,
+                  stats=None):
+    """FCN.forward training branch with the shipped backbone — fcn network.py:13-47: resnet101(deep_stem=True,
+    stem_width=64), plain output-stride-32 trunk, _FCNHead(2048) x32 and _FCNHead(1024) x16, CE, loss + 0.5*aux
+    (Dropout2d(0.1) disabled in the parity runs)"""
+    blocks = resnet_v1c_d8(data, sd, "backbone", layers, eps, momentum, True, stats, dilated=False)
+
+    def head(x, prefix):
+        fm = conv_bn_relu(x, sd, prefix + ".cbr", 1, 1, eps=eps, momentum=momentum, training=True, stats=stats)
+        return F.conv2d(fm, qw(sd[prefix + ".conv1x1.weight"]), sd[prefix + ".conv1x1.bias"])
+
+    lo, lo_aux = head(blocks[-1], "head"), head(blocks[-2], "aux_head")
+    pred = F.interpolate(lo, scale_factor=32, mode="bilinear", align_corners=True)
+    aux = F.interpolate(lo_aux, scale_factor=16, mode="bilinear", align_corners=True)
+    loss = F.cross_entropy(pred, label, ignore_index=ignore_label)
+    return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label), (lo, lo_aux)
+
+
 # --------------------------------------------------------------------------------------------------
 # PSPNet-R101_v1c dilated-8 — /root/reference/model/pspnet/ade.pspnet.R101_v1c/network.py:14-109
 # --------------------------------------------------------------------------------------------------

@@ -42,6 +42,15 @@ def fcn_case(N=2, HW=256, seed=304):
     return x, y, seed
 
 
+def fcn_r101_case(N=2, HW=128, seed=304, classes=21):
+    """the shipped FCN-32s (R101_v1c, VOC 21 classes, ignore 255) at a small size"""
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(N, 3, HW, HW, generator=g)
+    y = torch.randint(0, classes, (N, HW, HW), generator=g, dtype=torch.int64)
+    y[:, : HW // 10, :] = 255
+    return x, y, seed
+
+
 def pspnet_case(N=2, HW=96, seed=4, classes=150):
     """BASELINE configs[2] shape family (PSPNet R101_v1c dilated-8, ADE 150 classes, ignore -1), small spatial size"""
     g = torch.Generator().manual_seed(seed)

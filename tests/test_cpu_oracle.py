@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, dfn_case, psanet_case, OHEM_REGIMES
+from golden_cases import ohem_case, bisenet_case, fcn_case, fcn_r101_case, pspnet_case, dfn_case, psanet_case, OHEM_REGIMES
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "reference_outputs.json")))
@@ -98,6 +98,27 @@ def test_torch_oracle_fcn_r18_vs_golden():
         sd[k] = v.detach().clone()
     loss = torch_ref.fcn_r18_loss(x, y, sd)
     assert abs(float(loss) - GOLD["fcn_r18"]["loss"]) < 1e-5 * GOLD["fcn_r18"]["loss"]
+
+
+def test_torch_oracle_fcn_r101_vs_golden():
+    """the shipped FCN-32s R101_v1c: our module reproduces the reference construction (seed → same weights, same keys)
+    and the oracle restatement reproduces the live reference's loss / gradient norms"""
+    from oracle import torch_ref
+    from torchseg_b200.networks import FCN
+    x, y, seed = fcn_r101_case()
+    torch.manual_seed(seed)
+    m = FCN(21, torch.nn.CrossEntropyLoss(ignore_index=255), backbone="R101")
+    g = GOLD["fcn_r101"]
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert sum(p.numel() for p in m.parameters()) == g["n_params"] and len(sd) == g["n_state"]
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    loss, _ = torch_ref.fcn_r101_loss(x, y, sd)
+    assert abs(float(loss) - g["loss"]) < 1e-5 * g["loss"]
+    loss.backward()
+    for n, ref in g["grad_norms"].items():
+        assert abs(float(sd[n].grad.norm()) - ref) < 1e-4 * ref, n
 
 
 def test_torch_oracle_pspnet_vs_golden():

@@ -1,6 +1,6 @@
 """BNRefine (seg_oprs.py:143-162): defined by the reference for DFN but not instantiated by any shipped network, so it is
-not covered by the DFN step test. Same structure as RefineResidual without the 1x1 (validated on hardware); this
-teacher-forced test was written after the round's GPU budget was spent — non-strict xfail until its first green run."""
+not covered by the DFN step test. Same structure as RefineResidual without the 1x1 (validated on hardware); first
+green run: round-1 driver GPUTEST (x-passed); strict since round 2."""
 import pytest
 import torch
 
@@ -10,7 +10,6 @@ from test_gpu_bisenet import _sd_of, _prep, _rand, BN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(reason="not yet run on hardware (see module docstring)", strict=False)
 @pytest.mark.parametrize("has_relu", [True, False])
 def test_bn_refine_teacher_forced(cuda, has_relu):
     from torchseg_b200 import ops

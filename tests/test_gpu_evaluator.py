@@ -1,9 +1,8 @@
 """Evaluator (engine/evaluator.py) driving the libtsb eval-mode BiSeNet forward on the GPU: multi-scale + flip sliding
 evaluation with batched windows, against the same evaluator driving the oracle network on the CPU.
 
-Written after the round's GPU budget was spent: the pieces are validated separately (eval forward on the GPU:
-test_bisenet_eval_forward_matches_oracle; evaluator logic pixel-for-pixel vs the live reference on the CPU), this
-composition has not run on hardware yet — hence the non-strict xfail marker, to be removed after its first green run."""
+The pieces are also validated separately (eval forward on the GPU: test_bisenet_eval_forward_matches_oracle; evaluator
+logic pixel-for-pixel vs the live reference on the CPU). First green run: round-1 driver GPUTEST; strict since round 2."""
 import numpy as np
 import pytest
 import torch
@@ -13,7 +12,6 @@ pytestmark = pytest.mark.gpu
 BN = torch.nn.BatchNorm2d
 
 
-@pytest.mark.xfail(reason="composition not yet run on hardware (see module docstring)", strict=False)
 def test_sliding_eval_on_libtsb_bisenet(cuda):
     import torchseg_b200
     from torchseg_b200.engine.evaluator import Evaluator

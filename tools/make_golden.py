@@ -16,7 +16,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
 from oracle import reference_live as rl  # noqa: E402
-from golden_cases import ohem_case, bisenet_case, fcn_case, pspnet_case, dfn_case, psanet_case, OHEM_REGIMES  # noqa: E402
+from golden_cases import ohem_case, bisenet_case, fcn_case, fcn_r101_case, pspnet_case, dfn_case, psanet_case, OHEM_REGIMES  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -84,6 +84,23 @@ def main():
     aux = F.interpolate(aux_head(blocks[-2]), scale_factor=16, mode='bilinear', align_corners=True)
     ce = nn.CrossEntropyLoss(ignore_index=255)
     gold["fcn_r18"] = {"loss": float(ce(pred, y) + 0.5 * ce(aux, y))}
+
+    # the shipped FCN-32s R101_v1c (fcn network.py:13-47, train.py:45-47 criterion), Dropout2d disabled
+    fcn21 = rl.load_network('fcn/voc.fcn32s.R101_v1c', num_classes=21, aux_loss_ratio=0.5)
+    x, y, seed = fcn_r101_case()
+    torch.manual_seed(seed)
+    m = fcn21.FCN(21, nn.CrossEntropyLoss(reduction='mean', ignore_index=255), True, None, nn.BatchNorm2d)
+    for mod in m.modules():
+        if isinstance(mod, nn.Dropout2d):
+            mod.p = 0.0
+    m.train()
+    loss = m(x, y)
+    loss.backward()
+    gold["fcn_r101"] = {"loss": float(loss), "n_params": sum(p.numel() for p in m.parameters()),
+                        "n_state": len(m.state_dict()),
+                        "grad_norms": {n: float(p.grad.norm()) for n, p in m.named_parameters()
+                                       if n in ("backbone.conv1.0.weight", "backbone.layer4.2.conv3.weight",
+                                                "head.cbr.conv.weight", "head.conv1x1.weight", "aux_head.conv1x1.bias")}}
 
     # PSPNet-R101_v1c dilated-8 (BASELINE configs[2] family), Dropout2d disabled
     psp = rl.load_network('pspnet/ade.pspnet.R101_v1c', num_classes=150)

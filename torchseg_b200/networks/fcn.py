@@ -30,7 +30,8 @@ class FCN(nn.Module):
         self.criterion = criterion
         self.out_planes = out_planes
         self.aux_loss_ratio = aux_loss_ratio
-        self.ignore_label = ignore_label
+        # train.py:45-47 passes nn.CrossEntropyLoss(reduction='mean', ignore_index=255): its ignore_index wins
+        self.ignore_label = int(getattr(criterion, "ignore_index", ignore_label))
 
     def forward(self, data, label=None):
         blocks = self.backbone(data)

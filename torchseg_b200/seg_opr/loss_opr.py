@@ -25,14 +25,20 @@ class ProbOhemCrossEntropy2d(nn.Module):
             self.register_buffer("weight", torch.tensor(self.CITYSCAPES_WEIGHT, dtype=torch.float32))
         else:
             self.weight = None
+        self.debug_states = None   # tests / logging: set to a list to collect each call's device-side OHEM state words
+
+    def _record(self, loss):
+        if self.debug_states is not None and loss.grad_fn is not None:
+            self.debug_states.append(loss.grad_fn.saved_tensors[3])
+        return loss
 
     def forward(self, pred, target):
-        return ops.OhemCEFn.apply(pred, target, self.ignore_label, self.thresh, self.min_kept, self.weight)
+        return self._record(ops.OhemCEFn.apply(pred, target, self.ignore_label, self.thresh, self.min_kept, self.weight))
 
     def forward_lowres(self, logits_lo, target, num_classes):
         H, W = target.shape[-2:]
-        return ops.OhemUpCEFn.apply(logits_lo, target, H, W, num_classes, self.ignore_label, self.thresh,
-                                    self.min_kept, self.weight)
+        return self._record(ops.OhemUpCEFn.apply(logits_lo, target, H, W, num_classes, self.ignore_label, self.thresh,
+                                                 self.min_kept, self.weight))
 
 
 class SigmoidFocalLoss(nn.Module):
