@@ -29,6 +29,7 @@ STEP_GFLOP_PER_IMG = 338.1   # 3 x 116.00 - 2 x 4.933 (conv FLO
 METRIC = "images/sec training step (1024x1024, 19-class)"
 MODEL = "bisenet"            # --model pspnet: secondary line for BASELINE configs[2] (PSPNet-R101_v1c d8, ADE shape)
 WORKLOAD = "BiSeNet-R18 train step, 1024x1024, 19-class, OHEM (BASELINE configs[1])"
+CPU_SAMPLE_BATCH = 2         # the CPU arms time batch 2 @ 1024x1024 per step (one shape for cpu_baseline and --impl reference)
 
 
 def load_peaks():
@@ -207,6 +208,77 @@ def cpu_reference_steps(n, h, w, steps, warmup, threads):
     return n * len(times) / sum(times), float(loss.detach())
 
 
+def gpu_reference_steps(device, n, h, w, steps, warmup, mode):
+    """SURVEY §8d last row / BASELINE.md §3: the reference step (oracle/torch_ref.py restatement = the reference
+    modules' stock torch.nn lowering) on THIS GPU under cuDNN with cudnn.benchmark=True (train.py:35) and
+    torch.optim.SGD — the practical "reference GPU path". mode: 'fp32' (strict, TF32 off), 'tf32' (PyTorch's conv
+    default) or 'bf16' (torch.autocast + channels_last, the fastest stock-PyTorch configuration). The oracle is the thing
+    COMPARED AGAINST here, never part of the product path."""
+    from oracle import torch_ref
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.utils.init_func import init_weight
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = mode != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+    try:
+        torch.manual_seed(12345)
+        shell = BiSeNet(NUM_CLASSES, True, None, None, torch.nn.BatchNorm2d)
+        init_weight(shell.business_layer, torch.nn.init.kaiming_normal_, torch.nn.BatchNorm2d, 1e-5, 0.1, mode='fan_in',
+                    nonlinearity='relu')
+        sd = {}
+        for k, v in shell.state_dict().items():
+            v = v.detach().clone().to(device)
+            if mode == "bf16" and v.dim() == 4:
+                v = v.contiguous(memory_format=torch.channels_last)
+            sd[k] = v
+        params = []
+        for k, v in sd.items():
+            if v.is_floating_point() and "running" not in k:
+                v.requires_grad_(True)
+                params.append(v)
+        opt = torch.optim.SGD(params, lr=1e-2, momentum=0.9, weight_decay=5e-4)
+        imgs, gts = synth_batch(n, h, w, 7)
+        imgs, gts = imgs.to(device), gts.to(device)
+        if mode == "bf16":
+            imgs = imgs.contiguous(memory_format=torch.channels_last)
+        min_kept = n * h * w // 16
+        stats = {}
+
+        def one():
+            opt.zero_grad()
+            if mode == "bf16":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    lo, _ = torch_ref.bisenet_r18_forward(imgs, sd, 1e-5, 0.1, True, stats)
+                lo = [l.float() for l in lo]
+                import torch.nn.functional as F
+                loss = 0
+                for l, sc in zip(lo, (16, 8, 8)):   # losses in fp32, as autocast would run softmax / CE
+                    loss = loss + torch_ref.ohem_ce(F.interpolate(l, scale_factor=sc, mode="bilinear", align_corners=True),
+                                                    gts, IGNORE, 0.7, min_kept)
+            else:
+                loss, _ = torch_ref.bisenet_r18_loss(imgs, gts, sd, min_kept, stats=stats)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return dict(value=n / (ms / 1000.0), unit="images/sec", ms_per_step=ms, batch=n, steps=steps, warmup=warmup,
+                    final_loss=float(loss))
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+
+
 def pick_threads():
     """torch CPU ops do not scale to every hardware thread of a big host: calibrate on a tiny step and use the
     fastest of {all, 64, 32, 16} threads (reported as `cores`)."""
@@ -227,13 +299,15 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = pick_threads()
-    n, hw = 2, 1024
-    steps = min(args.steps, 5)  # bounded sample: each step is seconds of CPU work
-    ips, _ = cpu_reference_steps(n, hw, hw, steps, 1, threads)
-    sample = "oracle port of the reference step (fp32 NCHW torch.nn lowering), batch %d @ %dx%d, %d timed steps, %d threads" % (
-        n, hw, hw, steps, threads)
-    line = dict(impl="reference", metric=METRIC, value=ips, unit="images/sec", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1000.0 * n / ips, higher_is_better=True, scaling="weak", vs_baseline=None,
+    n, hw = CPU_SAMPLE_BATCH, 1024
+    # every one of the K timed steps (and W warm-up steps) is ONE step of the bounded sample: batch 2 @ 1024x1024, the
+    # reference's own per-GPU batch (config.py:82 / dataloader.py:53), ~3 s of CPU work each
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    ips, _ = cpu_reference_steps(n, hw, hw, steps, warmup, threads)
+    sample = "oracle port of the reference step (fp32 NCHW torch.nn lowering), batch %d @ %dx%d per step, %d warm-up + %d timed steps, %d threads" % (
+        n, hw, hw, warmup, steps, threads)
+    line = dict(impl="reference", metric=METRIC, value=ips, unit="images/sec", n_gpus=args.gpus, steps=steps,
+                warmup=warmup, ms_per_step=1000.0 * n / ips, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic",
                 config=dict(workload=WORKLOAD, batch_per_step=n, device="host CPU (bounded sample of the same workload)"),
                 cpu_baseline=dict(value=ips, unit="images/sec", cores=threads, kind="port", sample=sample),
@@ -255,7 +329,9 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="input size override (pspnet default 480, the reference shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
-                    help="experimental: time the step as ONE CUDA graph replay (engine.graph.GraphedTrainStep); default = eager launches")
+                    help="time the step as ONE CUDA graph replay (engine.graph.GraphedTrainStep); default = eager launches")
+    ap.add_argument("--default-stream", action="store_true",
+                    help="run on the legacy default stream (default: a non-blocking side stream, which whole-step graph capture needs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -271,6 +347,10 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", init_method="env://", device_id=device)
+    if not args.default_stream:
+        # everything (warm-up, timed regions, autograd's accumulation streams) lives on ONE non-default stream: a stream
+        # capture is invalidated by any work that touches the legacy default stream
+        torch.cuda.set_stream(torch.cuda.Stream(device=device))
     warmup = max(3, args.warmup)
     BATCH_PER_GPU = args.batch
     if args.model == "pspnet":
@@ -320,13 +400,26 @@ def main():
     for _ in range(warmup):
         loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
         it += 1
-    # ---------------- timed region 1 (`value`): the same step as ONE CUDA graph (single GPU; zero_grad → forward →
-    # backward → fused SGD captured once, torchseg_b200.engine.graph.GraphedTrainStep), inputs resident in HBM.
-    # Falls back to the eager numbers above when capture is unavailable (multi-GPU: the DDP side stream is not captured).
-    # (captured BEFORE the event-instrumented eager pass: a capture attempted after that pass is invalidated on this
-    # stack — tools/diag_graph2.py)
+
+    def timed_eager(nsteps):
+        nonlocal it
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        with ClockSampler(local) as clk_:
+            e0.record()
+            for _ in range(nsteps):
+                loss_ = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
+                it += 1
+            e1.record()
+            barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), clk_, _lib.launch_count() - n0, loss_
+
+    # ---------------- timed region 1 (`value`), CLEAN: no event instrumentation, inputs resident in HBM.
+    # Single GPU: the whole step (zero_grad → forward → backward → fused SGD) is ONE CUDA graph replay
+    # (torchseg_b200.engine.graph.GraphedTrainStep) unless --no-graph / capture is unavailable; multi-GPU: eager launches
+    # (the DDP side-stream all-reduce is not captured).
     gstep = None
-    ms = None
     if world == 1 and args.graph:
         from torchseg_b200.engine.graph import GraphedTrainStep
         set_lr(it)
@@ -334,6 +427,8 @@ def main():
         if gstep.graph is None:
             sys.stderr.write("bench: CUDA graph capture unavailable (%s); eager step timed instead\n" % gstep.error)
             gstep = None
+    ms_eager, clk_eager, launches_eager, loss = timed_eager(args.steps)
+    ms, clk, launches, final_loss = ms_eager, clk_eager, launches_eager, float(loss.item())
     if gstep is not None:
         static_in = gstep.static_inputs
         for _ in range(2):
@@ -342,7 +437,7 @@ def main():
             it += 1
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
+        with ClockSampler(local) as clk_g:
             e0.record()
             for _ in range(args.steps):
                 set_lr(it)
@@ -350,32 +445,18 @@ def main():
                 it += 1
             e1.record()
             barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        launches_graph = gstep.launches_per_step * args.steps
+        ms, clk = max_over_ranks(e0.elapsed_time(e1)), clk_g
+        launches = gstep.launches_per_step * args.steps
         final_loss = float(loss.item())
 
-    # ---------------- measurement pass A (eager launches): every conv launch bracketed by CUDA events on the launch
-    # stream → roofline.achieved; also the throughput of the un-graphed step
+    # ---------------- measurement pass B (separate, NOT part of `value`): every conv launch bracketed by CUDA events on
+    # the launch stream → roofline.achieved = algorithmic conv FLOPs / summed conv kernel time
+    prof_steps = min(args.steps, 5)
     ops.conv_prof.enable()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count()
-    with ClockSampler(local) as clk_eager:
-        e0.record()
-        for _ in range(args.steps):
-            loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
-            it += 1
-        e1.record()
-        barrier()
-    launches = _lib.launch_count() - launches0
-    ms_eager = max_over_ranks(e0.elapsed_time(e1))
-    launches_eager = launches
+    timed_eager(prof_steps)
     prof = ops.conv_prof.collect()
     ops.conv_prof.disable()
-    if ms is None:      # no graph: the eager pass IS timed region 1
-        ms, clk, final_loss = ms_eager, clk_eager, float(loss.item())
-    else:
-        launches = launches_graph
+
     def run_step(it_, *inputs):
         if gstep is not None:
             set_lr(it_)
@@ -411,20 +492,27 @@ def main():
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     assert bool(torch.isfinite(loss_host).all()), "non-finite loss in the e2e region"
 
+    if world > 1:      # all collective work is done: ranks > 0 leave, rank 0 reports (no rank spins in a barrier)
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0:
         peaks = load_peaks()
         n_img = BATCH_PER_GPU * world * args.steps
         value = n_img / (ms / 1000.0)
         e2e_v = n_img / (ms_e2e / 1000.0)
         # ALGORITHMIC conv FLOPs of the step (SURVEY §8d figure x images of this rank) over the measured duration of all
-        # conv launches of the region. prof["flops"] counts the launched shapes, which include the zero-padded
+        # conv launches of the instrumented pass. prof["flops"] counts the launched shapes, which include the zero-padded
         # channels of DFN's ragged layers (and is identical to the algorithmic figure for BiSeNet / PSPNet).
-        algo_flops = STEP_GFLOP_PER_IMG * 1e9 * BATCH_PER_GPU * args.steps
+        algo_flops = STEP_GFLOP_PER_IMG * 1e9 * BATCH_PER_GPU * prof_steps
         conv_tf = min(prof["flops"], algo_flops) / max(prof["ms"], 1e-9) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-        if os.path.exists(tpath) and MODEL == "bisenet":  # DRAM bytes of the same launches from the committed ncu pass (per step)
-            traffic = json.load(open(tpath)).get("conv_dram_bytes_per_step")
+        traffic_src = None
+        for cand in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", cand)
+            if os.path.exists(tpath) and MODEL == "bisenet":  # DRAM bytes of the same launches from the committed ncu pass (per step)
+                traffic = json.load(open(tpath)).get("conv_dram_bytes_per_step")
+                traffic_src = "profiles/" + cand
+                break
         line = {
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -445,22 +533,35 @@ def main():
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": conv_tf / peaks["tflops"], "traffic": traffic,
-                         "traffic_note": "dram__bytes_read+write summed over the conv launches of ONE step (profiles/r01_conv_traffic.json); algorithmic minimum ~5.9 GB/step",
-                         "flops_per_step": min(prof["flops"], algo_flops) / args.steps,
-                         "launched_flops_per_step": prof["flops"] / args.steps,
-                         "kernel": "tcgen05 implicit-GEMM conv kernels (igemm_v2_kernel fprop/dgrad/stem + wgrad_rows_kernel/wgrad_mnmajor_kernel), all launches of the step",
-                         "launches": prof["launches"], "kernel_ms_per_step": prof["ms"] / args.steps,
+                         "traffic_note": "dram__bytes_read+write summed over the conv launches of ONE step (%s); algorithmic minimum ~5.9 GB/step" % traffic_src,
+                         "flops_per_step": min(prof["flops"], algo_flops) / prof_steps,
+                         "launched_flops_per_step": prof["flops"] / prof_steps,
+                         "kernel": "tcgen05 implicit-GEMM conv kernels (igemm_v2_kernel fprop/dgrad/stem + wgrad kernels), all launches of the step",
+                         "launches": prof["launches"], "kernel_ms_per_step": prof["ms"] / prof_steps,
+                         "measured_in": "separate instrumented pass of %d eager steps (not the `value` region)" % prof_steps,
                          "peak_source": peaks["src"]},
         }
-        if not args.no_cpu_baseline and MODEL == "bisenet":
+        if world == 1 and not args.no_cpu_baseline and MODEL == "bisenet":
+            # the reference step on THIS GPU under stock PyTorch + cuDNN (SURVEY §8d last row): the numbers the kernels
+            # must beat; strict fp32 is the parity configuration, bf16 autocast + channels_last the fastest stock one
+            ref_gpu = {}
+            nb = BATCH_PER_GPU
+            for mode in ("fp32", "bf16"):
+                try:
+                    ref_gpu[mode] = gpu_reference_steps(device, nb, H, W, 3, 2, mode)
+                except torch.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    nb = max(2, nb // 2)
+                    ref_gpu[mode] = gpu_reference_steps(device, nb, H, W, 3, 2, mode)
+            best = max(v["value"] for v in ref_gpu.values())
+            line["reference_gpu"] = {"kind": "port", "what": "oracle restatement of the reference step (stock torch.nn + cuDNN, cudnn.benchmark=True, torch.optim.SGD) on the same B200",
+                                     "fp32": ref_gpu["fp32"], "bf16_autocast_channels_last": ref_gpu["bf16"],
+                                     "speedup_vs_fp32": value / ref_gpu["fp32"]["value"], "speedup_vs_best": value / best}
             threads = pick_threads()
-            ips, _ = cpu_reference_steps(2, 512, 512, 2, 1, threads)
+            ips, _ = cpu_reference_steps(CPU_SAMPLE_BATCH, 1024, 1024, 2, 1, threads)
             line["cpu_baseline"] = {"value": ips, "unit": "images/sec", "cores": threads, "kind": "port",
-                                    "sample": "oracle port of the reference step, batch 2 @ 512x512, 1 warm-up + 2 timed steps"}
+                                    "sample": "oracle port of the reference step, batch %d @ 1024x1024, 1 warm-up + 2 timed steps" % CPU_SAMPLE_BATCH}
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
