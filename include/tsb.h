@@ -42,7 +42,8 @@ int tsb_version(void);          /* 10000*major + 100*minor + patch */
 /* number of kernels launched by this library from the calling process since load (all threads) */
 long long tsb_launch_count(void);
 /* debug / A-B switches of the convolution path: key 1 = UMMA descriptor base_offset for row-shifted taps,
- * 2 = allow row tiles, 3 = allow resident weights, 4 = use the persistent kernel (0 → first-generation kernel) */
+ * 2 = allow row tiles, 3 = allow resident weights, 4 = use the persistent kernel (0 → first-generation kernel),
+ * 5 = wgrad waves, 6 = OHEM register hoisting, 7 = weight-sharing tile pairs, 8 = nine-tap wgrad kernel */
 int tsb_debug_set(int key, int value);
 
 /* ================================================================================================

@@ -85,13 +85,18 @@ def test_bisenet_full_size_step_matches_oracle_cuda(cuda):
     print("full-size N=%d: loss %.6f oracle %.6f rel %.2e" % (N, loss.item(), loss_ref_v, rel))
     assert rel < 1e-2, (loss.item(), loss_ref_v)
 
-    # OHEM: kept count per head (aux0, aux1, main — the order the network calls the criterion in)
+    # OHEM: kept count per head (aux0, aux1, main — the order the network calls the criterion in). The whole-step counts
+    # cannot be bit-equal: the two networks' logits differ by bf16-level noise, so the (few thousand) pixels whose p lies
+    # within that noise of the 0.7 threshold flip. They must agree to 1e-3 here; the EXACT kept-set check at this size is
+    # the teacher-forced test below (same logits into both).
+    failures = []
     assert len(crit.debug_states) == 3
     for i, (st, (kept, thr)) in enumerate(zip(crit.debug_states, kept_ref)):
         d = ops.ohem_state_dict(st)
         n_kept = d["kept"]
         print("head %d: kept %d (oracle %d), threshold %.6f (oracle %.6f)" % (i, n_kept, kept, d["T"] if d["active"] else 0.7, thr))
-        assert n_kept == kept, (i, n_kept, kept)
+        if abs(n_kept - kept) > 1e-3 * kept:
+            failures.append(("kept", i, n_kept, kept))
 
     # gradients: business layers tight, whole network aligned
     business = ("spatial_path.", "global_context.", "arms.", "refines.", "heads.", "ffm.")
@@ -108,11 +113,92 @@ def test_bisenet_full_size_step_matches_oracle_cuda(cuda):
             cos_bad.append((n, round(cos, 4)))
     worst.sort(reverse=True)
     print("worst gradient norm_err:", [(n, round(e, 4)) for e, n in worst[:8]])
-    assert not bad, "business-layer gradient norm_err > 2e-2: %s" % bad[:10]
-    assert not cos_bad, "gradient cosine < 0.95: %s" % cos_bad[:10]
+    print("business-layer norm_err > 2e-2:", bad[:20])
+    print("cosine < 0.95:", cos_bad[:20])
 
     # BN running statistics (momentum 0.1, unbiased variance)
     msd = model.state_dict()
+    stat_bad = []
     for k, v in stats.items():
         e = float((msd[k].float().cpu() - v).abs().max() / v.abs().max().clamp_min(1e-6))
-        assert e < 1e-2, (k, e)
+        if e >= 1e-2:
+            stat_bad.append((k, round(e, 4)))
+    print("running statistics off by > 1e-2:", stat_bad[:10])
+    assert not failures, failures
+    assert not bad, "business-layer gradient norm_err > 2e-2: %s" % bad[:10]
+    assert not cos_bad, "gradient cosine < 0.95: %s" % cos_bad[:10]
+    assert not stat_bad, stat_bad[:10]
+
+
+def test_ohem_full_size_kept_set_teacher_forced(cuda):
+    """OHEM at the BASELINE size (16 x 19 x 1024 x 1024 after the x8 upsample) on IDENTICAL low-resolution logits: the
+    fused-upsample kernels' kept set against torch's softmax / sort / threshold (the oracle restatement of
+    loss_opr.py:68-98) evaluated on the same GPU. Two regimes: A (random logits: threshold 0.7, nearly all valid pixels
+    kept) and B (confident logits: fewer than min_kept pixels below 0.7, so the threshold is the k-th smallest p).
+    The pinned exp_det / ATen-order bilinear differ from torch's exp / FMA-contracted CUDA upsample in the last ulp, so a
+    pixel whose p straddles the threshold within 1 ulp may flip: at most a handful out of 16.8 M (reported)."""
+    from torchseg_b200 import ops
+    from oracle import torch_ref
+    N, C, h, w, s = 16, 19, 128, 128, 8
+    H, W = h * s, w * s
+    min_kept = N * H * W // 16
+    g = torch.Generator().manual_seed(31)
+    for regime in ("A", "B"):
+        lo = torch.randn(N, C, h, w, generator=g)
+        if regime == "A":
+            labels = make_labels(N, H, W, C, 255, g).to(cuda)
+        else:
+            # confident logits on smooth label regions (64 x 64 low-res cells per class block): only the ~3 % of pixels
+            # on block borders fall below 0.7 — fewer than min_kept = 1/16 of the pixels — so T = k-th smallest p > 0.7
+            blocks = torch.randint(0, C, (N, h // 64, w // 64), generator=g)
+            lab_lo = blocks.repeat_interleave(64, 1).repeat_interleave(64, 2)
+            lo = lo + 9.0 * torch.nn.functional.one_hot(lab_lo, C).permute(0, 3, 1, 2).float()
+            labels = lab_lo.repeat_interleave(s, 1).repeat_interleave(s, 2).contiguous()
+            labels[:, : H // 10, :] = 255
+            labels = labels.to(cuda)
+        lo_d = ops.nhwc_zeros(N, C, h, w, dtype=torch.float32, device=cuda, cs=32)
+        lo_d.copy_(lo.to(cuda))
+        lo_d.requires_grad_(True)
+        loss = ops.OhemUpCEFn.apply(lo_d, labels, H, W, C, 255, 0.7, min_kept, None)
+        _, _, p, state, _ = loss.grad_fn.saved_tensors
+        st = ops.ohem_state_dict(state)
+        T = torch.tensor(st["T"], dtype=torch.float32, device=cuda)
+        valid = labels.reshape(-1) != 255
+        kept = valid & ((p <= T) if st["active"] else torch.ones_like(valid))
+        up = F.interpolate(lo.to(cuda), scale_factor=s, mode="bilinear", align_corners=True)
+        loss_ref, kept_ref, thr_ref = torch_ref.ohem_ce(up, labels, 255, 0.7, min_kept, return_aux=True)
+        del up
+        mism = int((kept != kept_ref.reshape(-1)).sum())
+        print("regime %s: kept %d (oracle %d), mismatching pixels %d, T %.9g (oracle %.9g), loss %.6f (oracle %.6f)" % (
+            regime, int(kept.sum()), int(kept_ref.sum()), mism, st["T"], thr_ref, loss.item(), float(loss_ref)))
+        # torch's exp / FMA-contracted upsample vs the pinned recipe: <= a few ulp in p. In regime B ~1e6 pixels sit
+        # within 5e-3 of T (density ~2e8 per unit p, i.e. ~12 pixels per ulp), so a few dozen may straddle it
+        assert mism <= (8 if regime == "A" else 96), (regime, mism)
+        assert abs(st["T"] - thr_ref) <= 1e-6 * max(1.0, abs(thr_ref)), (st["T"], thr_ref)
+        assert abs(loss.item() - float(loss_ref)) < 1e-4 * abs(float(loss_ref))
+        if regime == "B":
+            assert st["active"] and st["T"] > 0.7 and abs(int(kept.sum()) - min_kept) <= 96
+            # ... and BIT-EXACT against the C oracle (same pinned exp / bilinear recipe, oracle/tsb_oracle.c) at the full
+            # 1024 x 1024 resolution on the first 4 images: p, T and the kept set must be identical
+            import numpy as np
+            from oracle import c_oracle
+            n4 = 4
+            mk4 = n4 * H * W // 16
+            lo4 = ops.nhwc_zeros(n4, C, h, w, dtype=torch.float32, device=cuda, cs=32)
+            lo4.copy_(lo[:n4].to(cuda))
+            lab4 = labels[:n4].contiguous()
+            loss4 = ops.OhemUpCEFn.apply(lo4.requires_grad_(True), lab4, H, W, C, 255, 0.7, mk4, None)
+            _, _, p4, state4, _ = loss4.grad_fn.saved_tensors
+            st4 = ops.ohem_state_dict(state4)
+            lo_np = lo4.detach().permute(0, 2, 3, 1).cpu().numpy()           # [n, h, w, C] view of the NHWC buffer
+            lo_np = np.ascontiguousarray(np.pad(lo_np, ((0, 0), (0, 0), (0, 0), (0, 32 - C))))
+            up4 = c_oracle.bilinear_nhwc_to_nchw(lo_np, C, H, W)
+            ref4 = c_oracle.ohem(up4, lab4.cpu().numpy(), 255, 0.7, mk4)
+            p4 = p4.cpu().numpy()
+            assert st4["active"] == ref4["active"]
+            assert np.float32(st4["T"]).tobytes() == np.float32(ref4["T"]).tobytes(), (st4["T"], ref4["T"])
+            assert np.array_equal(p4.view(np.uint32), ref4["p"].view(np.uint32)), "p_target bits differ from the C oracle"
+            kept4 = (lab4.cpu().numpy().reshape(-1) != 255) & (p4 <= np.float32(st4["T"]))
+            assert np.array_equal(kept4, ref4["kept"])
+            assert abs(loss4.item() - ref4["loss"]) < 1e-5 * abs(ref4["loss"])
+            print("regime B, 4 x 19 x 1024 x 1024 vs the C oracle: p bits, T bits and kept set (%d pixels) identical" % int(kept4.sum()))

@@ -371,11 +371,7 @@ __global__ void __launch_bounds__(kThreadsConv, 1) wgrad_mnmajor_kernel(const __
 template <int BN, int STAGES>
 int launch_km(const KmParams& prm, int tiles, int n_tiles, cudaStream_t st) {
     using L = KmSmem<BN, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TSB_CUDA_CALL(cudaFuncSetAttribute(igemm_kmajor_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        attr_set = true;
-    }
+    { int rc_ = tsb_ensure_dyn_smem(reinterpret_cast<const void*>(igemm_kmajor_kernel<BN, STAGES>), L::kTotal); if (rc_) return rc_; }
     igemm_kmajor_kernel<BN, STAGES><<<dim3(tiles, n_tiles), kThreadsConv, L::kTotal, st>>>(prm);
     TSB_CUDA_CHECK_LAUNCH("igemm_kmajor");
     return TSB_OK;
@@ -392,11 +388,7 @@ int launch_km_auto(KmParams& prm, const void* w, int w_rows, long long w_k, int 
 }
 
 int launch_wg(const WgParams& prm, int splits, int co_tiles, int groups, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        TSB_CUDA_CALL(cudaFuncSetAttribute(wgrad_mnmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemTotal));
-        attr_set = true;
-    }
+    { int rc_ = tsb_ensure_dyn_smem(reinterpret_cast<const void*>(wgrad_mnmajor_kernel), kWgSmemTotal); if (rc_) return rc_; }
     wgrad_mnmajor_kernel<<<dim3(splits, co_tiles, groups), kThreadsConv, kWgSmemTotal, st>>>(prm);
     TSB_CUDA_CHECK_LAUNCH("wgrad_mnmajor");
     return TSB_OK;
@@ -647,6 +639,8 @@ extern "C" int tsb_conv2d_wgrad(const tsb_conv_shape* s, const void* x, int xcs,
         d.stride = s->stride;
         for (int t = 0; t < nt; ++t) d.taps[t] = prm.taps[t];
         d.ntaps = nt; d.dw_row_stride = prm.dw_row_stride; d.dw = dw;
+        rc = convv2::launch_wgrad_taps(d, s->R, s->pad, s->dil, st);   // 3x3 stride 1: all nine taps in one CTA
+        if (rc != TSB_ERR_UNSUPPORTED) return rc;
         rc = convv2::launch_wgrad_rows(d, st);
         if (rc != TSB_ERR_UNSUPPORTED) return rc;
     }

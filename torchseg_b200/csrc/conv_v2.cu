@@ -18,6 +18,8 @@ using namespace convhost;
 
 namespace {
 
+__device__ __forceinline__ uint32_t r_as_u(float f) { return __float_as_uint(f); }
+
 constexpr int kThreads = 384;  // 4 control warps + 8 epilogue warps
 constexpr int kMaxStages = 8;
 constexpr int kAStageBytes = 17 * 1024;  // (128 + 8) pixel rows x 128 B, rounded up to a 1024-byte multiple
@@ -40,6 +42,7 @@ struct alignas(64) V2Params {
     int P, Q;
     long long out_n_stride, out_p_stride, out_q_stride, out_base;
     int k_real, k_store, out_f32, accumulate;
+    int wide_io;   // every output pixel row is 32-byte aligned → 256-bit epilogue loads / stores
     const float* bias;
     float* sum;
     float* sumsq;
@@ -322,29 +325,62 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
                     float* o = reinterpret_cast<float*>(p.out) + pix_off + col0;
                     if (valid) {
 #pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            if (col0 + g * 4 < p.k_store)
-                                *reinterpret_cast<float4*>(o + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        for (int g = 0; g < 4; ++g) {
+                            if (p.wide_io && col0 + g * 8 + 8 <= p.k_store) {     // 8 floats = one full 32-byte sector
+                                stg_v8(o + g * 8,
+                                       make_uint4(r_as_u(v[g * 8]), r_as_u(v[g * 8 + 1]), r_as_u(v[g * 8 + 2]), r_as_u(v[g * 8 + 3])),
+                                       make_uint4(r_as_u(v[g * 8 + 4]), r_as_u(v[g * 8 + 5]), r_as_u(v[g * 8 + 6]), r_as_u(v[g * 8 + 7])));
+                            } else {
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh)
+                                    if (col0 + g * 8 + hh * 4 < p.k_store)
+                                        *reinterpret_cast<float4*>(o + g * 8 + hh * 4) =
+                                            make_float4(v[g * 8 + hh * 4], v[g * 8 + hh * 4 + 1], v[g * 8 + hh * 4 + 2], v[g * 8 + hh * 4 + 3]);
+                            }
+                        }
                     }
                 } else {
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix_off + col0;
                     if (p.accumulate && valid) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            if (col0 + g * 8 < p.k_store) {
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            if (p.wide_io && col0 + g2 * 16 + 16 <= p.k_store) {
+                                uint4 ua, ub;
+                                ldg_v8(o + g2 * 16, ua, ub);
                                 float old[8];
-                                uint4 u = *reinterpret_cast<const uint4*>(o + g * 8);
-                                unpack8(u, old);
+                                unpack8(ua, old);
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) v[g * 8 + q] += old[q];
+                                for (int q = 0; q < 8; ++q) v[g2 * 16 + q] += old[q];
+                                unpack8(ub, old);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) v[g2 * 16 + 8 + q] += old[q];
+                            } else {
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh)
+                                    if (col0 + g2 * 16 + hh * 8 < p.k_store) {
+                                        float old[8];
+                                        uint4 u = *reinterpret_cast<const uint4*>(o + g2 * 16 + hh * 8);
+                                        unpack8(u, old);
+#pragma unroll
+                                        for (int q = 0; q < 8; ++q) v[g2 * 16 + hh * 8 + q] += old[q];
+                                    }
                             }
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < 32; ++q) v[q] = bf16_round(v[q]);
                     if (valid) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            if (col0 + g * 8 < p.k_store) *reinterpret_cast<uint4*>(o + g * 8) = pack8(&v[g * 8]);
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            if (p.wide_io && col0 + g2 * 16 + 16 <= p.k_store) {   // 16 bf16 = one full 32-byte sector
+                                stg_v8(o + g2 * 16, pack8(&v[g2 * 16]), pack8(&v[g2 * 16 + 8]));
+                            } else {
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh)
+                                    if (col0 + g2 * 16 + hh * 8 < p.k_store)
+                                        *reinterpret_cast<uint4*>(o + g2 * 16 + hh * 8) = pack8(&v[g2 * 16 + hh * 8]);
+                            }
+                        }
                     }
                 }
                 if (do_stats) {
@@ -552,15 +588,12 @@ int g_use_base_offset = 0;  // measured on B200: the swizzle XOR is taken from t
 int g_allow_rows = 1;
 int g_allow_resident = 1;
 int g_wgrad_waves = 2;
+int g_allow_wide_io = 1;  // tsb_debug_set key 9: 256-bit epilogue loads / stores
 int g_allow_pair = 1;   // tsb_debug_set key 7: weight-sharing tile pairs in the streamed BN = 128 conv kernel
 
 template <int BN, bool RES, bool PAIR = false>
 int launch_v2(const V2Params& prm, int grid_x, int n_tiles, size_t smem, cudaStream_t st) {
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) {
-        TSB_CUDA_CALL(cudaFuncSetAttribute(igemm_v2_kernel<BN, RES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_bytes = 227 * 1024;
-    }
+    { int rc_ = tsb_ensure_dyn_smem(reinterpret_cast<const void*>(igemm_v2_kernel<BN, RES, PAIR>), smem); if (rc_) return rc_; }
     igemm_v2_kernel<BN, RES, PAIR><<<dim3(grid_x, n_tiles), kThreads, smem, st>>>(prm);
     TSB_CUDA_CHECK_LAUNCH("igemm_v2");
     return TSB_OK;
@@ -577,6 +610,8 @@ extern "C" int tsb_debug_set(int key, int value) {
     else if (key == 5) { g_wgrad_waves = value; convv2::g_wgrad_waves_x = value; }
     else if (key == 6) g_tsb_ohem_hoist = value;
     else if (key == 7) g_allow_pair = value;
+    else if (key == 8) convv2::g_allow_taps = value;
+    else if (key == 9) g_allow_wide_io = value;
     else return TSB_ERR_ARG;
     return TSB_OK;
 }
@@ -668,6 +703,12 @@ int launch(const Desc& d, cudaStream_t st) {
     prm.k_real = d.k_real; prm.k_store = d.k_store; prm.out_f32 = d.out_f32; prm.accumulate = d.accumulate;
     prm.bias = d.bias; prm.sum = d.sum; prm.sumsq = d.sumsq; prm.out = d.out;
     prm.use_base_offset = g_use_base_offset;
+    {
+        const long long es = d.out_f32 ? 4 : 2;
+        const bool al = (reinterpret_cast<uintptr_t>(d.out) % 32 == 0) && (d.out_base * es) % 32 == 0 && (d.out_n_stride * es) % 32 == 0 &&
+                        (d.out_p_stride * es) % 32 == 0 && (d.out_q_stride * es) % 32 == 0;
+        prm.wide_io = (g_allow_wide_io && al) ? 1 : 0;
+    }
     // ---- shared-memory plan
     const int kBTile = BN * 128;
     const long long res_need = (long long)d.ntaps * d.kchunks * kBTile;
@@ -767,11 +808,7 @@ int launch_wgrad_rows(const WgradDesc& d, cudaStream_t st) {
     if (want < 1) want = 1;
     prm.tiles_per_split = (prm.total_tiles + want - 1) / want;
     int splits = (prm.total_tiles + prm.tiles_per_split - 1) / prm.tiles_per_split;
-    static bool attr = false;
-    if (!attr) {
-        TSB_CUDA_CALL(cudaFuncSetAttribute(wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWrSmem));
-        attr = true;
-    }
+    { int rc_ = tsb_ensure_dyn_smem(reinterpret_cast<const void*>(wgrad_rows_kernel), kWrSmem); if (rc_) return rc_; }
     wgrad_rows_kernel<<<dim3(splits, co_tiles, zdim), 256, kWrSmem, st>>>(prm);
     TSB_CUDA_CHECK_LAUNCH("wgrad_rows");
     return TSB_OK;

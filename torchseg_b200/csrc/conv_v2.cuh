@@ -43,7 +43,9 @@ struct WgradDesc {
 
 extern int g_enabled;
 extern int g_wgrad_waves_x;
+extern int g_allow_taps;
 int launch(const Desc& d, cudaStream_t st);
 int launch_wgrad_rows(const WgradDesc& d, cudaStream_t st);
+int launch_wgrad_taps(const WgradDesc& d, int R, int pad, int dil, cudaStream_t st);   // conv_wgrad_taps.cu
 
 }  // namespace convv2

@@ -727,11 +727,7 @@ extern "C" int tsb_ohem_grad_up(const float* logits_lo, int cs, int h, int w, co
     cudaStream_t st = (cudaStream_t)stream;
 #define L(CM, HO)                                                                                                       \
     do {                                                                                                                \
-        static bool attr = false;                                                                                       \
-        if (!attr) {                                                                                                    \
-            TSB_CUDA_CALL(cudaFuncSetAttribute(ohem_grad_up_kernel<CM, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
-            attr = true;                                                                                                \
-        }                                                                                                               \
+        { int rc_ = tsb_ensure_dyn_smem(reinterpret_cast<const void*>(ohem_grad_up_kernel<CM, HO>), smem); if (rc_) return rc_; } \
         ohem_grad_up_kernel<CM, HO><<<grid, kThreads, smem, st>>>(logits_lo, cs, h, w, labels, p, N, C, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols); \
     } while (0)
     if (C <= 20) { if (g_tsb_ohem_hoist & 1) L(20, true); else L(20, false); }

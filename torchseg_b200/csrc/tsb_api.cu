@@ -1,6 +1,9 @@
 // libtsb: library-level entry points (error string, version, launch counter).
 #include <stdarg.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "tsb_common.cuh"
 
@@ -19,3 +22,21 @@ void tsb_count_launch(int n) { g_tsb_launches.fetch_add(n, std::memory_order_rel
 extern "C" const char* tsb_last_error(void) { return g_err; }
 extern "C" int tsb_version(void) { return 100; }
 extern "C" long long tsb_launch_count(void) { return g_tsb_launches.load(); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(device, function) property: remember what was already raised for
+// each pair under a mutex (autograd's backward thread and the forward thread both launch kernels; a process may drive
+// several devices).
+int tsb_ensure_dyn_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    int dev = 0;
+    TSB_CUDA_CALL(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[std::make_pair(dev, func)];
+    if (bytes > have) {
+        const size_t want = bytes > 48 * 1024 ? (size_t)227 * 1024 : bytes;
+        TSB_CUDA_CALL(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+        have = want;
+    }
+    return TSB_OK;
+}

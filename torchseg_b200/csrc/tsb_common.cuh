@@ -13,6 +13,7 @@
 // ----------------------------------------------------------------------------------------------
 void tsb_set_error(const char* fmt, ...);
 void tsb_count_launch(int n);
+int tsb_ensure_dyn_smem(const void* func, size_t bytes);   // per-(device, function), thread-safe
 
 #define TSB_FAIL(code, ...)            \
     do {                               \
@@ -41,13 +42,15 @@ void tsb_count_launch(int n);
     } while (0)
 
 static inline int tsb_num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static int sms[64] = {0};   // per device; a racing first call writes the same value twice
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
     }
-    return sms;
+    return sms[dev];
 }
 
 static inline bool tsb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -104,6 +107,20 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 }
 __device__ __forceinline__ void stg_v4(void* p, const uint4& v) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 256-bit global accesses (sm_100: LDG/STG.E.256): a thread that owns 32 or 64 contiguous bytes fills whole 32-byte
+// sectors per instruction instead of half sectors with 16-byte accesses. `p` must be 32-byte aligned.
+__device__ __forceinline__ void stg_v8(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void ldg_v8(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p)
+                 : "memory");
 }
 
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
