@@ -4,7 +4,7 @@ The product path has NO fallback: if the library is missing or a call fails, a R
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtsb.so")
@@ -72,8 +72,9 @@ _SIGS = {
     "tsb_sgd_flat_pack": [P, P, P, L, P, P, P, I, F, F, I, P, P],
     "tsb_pack_wt_multi": [P, P, P, P, I, I, P],
     "tsb_sigmoid_focal_fwd_bwd": [P, I, P, L, I, F, F, P, P, P],
+    "tsb_p2p_allreduce_sum": [P, I, P, I, I, c_uint, I, I, P, P, P],
 }
-EXPORTS = sorted(list(_SIGS) + ["tsb_last_error", "tsb_version", "tsb_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["tsb_last_error", "tsb_version", "tsb_launch_count", "tsb_p2p_buffer_bytes"])
 
 _lib = None
 
@@ -95,6 +96,8 @@ def lib():
         h.tsb_last_error.argtypes = []
         h.tsb_version.restype = c_int
         h.tsb_launch_count.restype = c_longlong
+        h.tsb_p2p_buffer_bytes.restype = c_size_t
+        h.tsb_p2p_buffer_bytes.argtypes = [I, I, I]
         # developer A/B switches (include/tsb.h tsb_debug_set): TSB_DEBUG_SET="6=0,5=2"
         for kv in filter(None, os.environ.get("TSB_DEBUG_SET", "").split(",")):
             k, v = kv.split("=")

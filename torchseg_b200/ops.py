@@ -200,17 +200,81 @@ def _notify(*params):
             grad_ready_hook(p)
 
 # process group for SyncBN statistics (set by apex_shim.parallel.SyncBatchNorm / DistributedDataParallel)
-_sync = {"group": None, "world": 1}
+_sync = {"group": None, "world": 1, "p2p": None, "p2p_tried": False}
 
 
 def set_sync_group(group, world):
     _sync["group"], _sync["world"] = group, world
+    if world <= 1:
+        _sync["p2p"], _sync["p2p_tried"] = None, False
 
 
-def _allreduce_stats(buf):
-    if _sync["world"] > 1:
+class _PeerExchange(object):
+    """SyncBN statistics exchange over NVLink peer memory (csrc/p2p.cu, tsb_p2p_allreduce_sum): one symmetric buffer per
+    rank (torch symmetric memory supplies the allocation and the peer-mapped addresses — plumbing only), ONE small
+    kernel per exchange instead of an NCCL all-reduce. All ranks must issue the same exchanges in the same order."""
+    NSLOTS = 64
+    SLOT_FLOATS = 4096      # 2 x 2048 channels (ResNet-101 layer4)
+
+    def __init__(self, group, world, device):
         import torch.distributed as dist
-        dist.all_reduce(buf, group=_sync["group"])
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.world = world
+        self.rank = dist.get_rank(pg)
+        nbytes = int(_lib.lib().tsb_p2p_buffer_bytes(world, self.NSLOTS, self.SLOT_FLOATS))
+        assert nbytes > 0
+        self.buf = symm.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, pg.group_name)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(ptrs) == world and all(ptrs)
+        self.peers = (ctypes.c_ulonglong * world)(*ptrs)
+        self.seq = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=pg)      # every rank's buffer is zeroed before anybody's first exchange can write into it
+
+    def allreduce(self, buf, acc_hi=None, acc_lo=None):
+        self.seq += 1
+        call("tsb_p2p_allreduce_sum", ptr(buf), buf.numel(), ctypes.cast(self.peers, ctypes.c_void_p), self.rank, self.world,
+             self.seq & 0xffffffff or 1, self.NSLOTS, self.SLOT_FLOATS, ptr(acc_hi), ptr(acc_lo), stream())
+
+
+def _peer_exchange(device):
+    """the NVLink exchange object, or None (single process, CPU / gloo, TSB_SYNCBN_P2P=0, no symmetric memory)"""
+    if _sync["world"] <= 1 or device.type != "cuda":
+        return None
+    if not _sync["p2p_tried"]:
+        _sync["p2p_tried"] = True
+        import os
+        if os.environ.get("TSB_SYNCBN_P2P", "1") != "0":
+            try:
+                _sync["p2p"] = _PeerExchange(_sync["group"], _sync["world"], device)
+            except Exception as e:  # noqa: BLE001 — no NVLink P2P / symmetric memory on this box: keep NCCL
+                import sys
+                sys.stderr.write("torchseg_b200: NVLink SyncBN exchange unavailable (%s: %s); using NCCL all-reduce\n" % (
+                    type(e).__name__, str(e).split("\n")[0][:200]))
+                _sync["p2p"] = None
+    return _sync["p2p"]
+
+
+def _allreduce_stats(buf, acc_hi=None, acc_lo=None):
+    """sum the packed per-channel statistics over the SyncBN group, in place. acc_hi / acc_lo (backward): the LOCAL
+    halves are first accumulated into the parameter gradients (dgamma += buf[1], dbeta += buf[0]). Returns True when
+    that accumulation was done here."""
+    if _sync["world"] <= 1:
+        return False
+    x = _peer_exchange(buf.device)
+    n = buf.numel()
+    if x is not None and n % 4 == 0 and n <= x.SLOT_FLOATS and buf.is_contiguous():
+        x.allreduce(buf, acc_hi, acc_lo)
+        return acc_hi is not None
+    import torch.distributed as dist
+    if acc_hi is not None:
+        acc_hi.add_(buf[1])   # local sums must be taken before the all-reduce
+        acc_lo.add_(buf[0])
+    dist.all_reduce(buf, group=_sync["group"])
+    return acc_hi is not None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -415,14 +479,13 @@ class ConvBNActFn(torch.autograd.Function):
         direct = _direct_grad(w) and _direct_grad(gamma) and _direct_grad(beta)
         fold = direct and _sync["world"] == 1   # single GPU: the accumulation is folded into tsb_bn_bwd_apply
         if direct:
-            if not fold:
-                gamma.grad.add_(red[1])   # local sums must be taken before the SyncBN all-reduce
-                beta.grad.add_(red[0])
             dgamma = dbeta = None
+            # multi-GPU: the exchange kernel adds the LOCAL sums to gamma.grad / beta.grad before it reduces
+            _allreduce_stats(red, None if fold else gamma.grad, None if fold else beta.grad)
         else:
             dgamma = red[1].clone()
             dbeta = red[0].clone()
-        _allreduce_stats(red)
+            _allreduce_stats(red)
         draw = nhwc_empty(N, K, P, Q, device=dev)
         dres = nhwc_empty(N, K, P, Q, device=dev) if has_res else None
         call("tsb_bn_bwd_apply", ptr(dy), cs_of(dy), y_mask, K, ptr(raw), K, ptr(aux[0]), ptr(aux[1]), ptr(gamma), ptr(red[0]),
@@ -517,11 +580,8 @@ class StemPairFn(torch.autograd.Function):
                  ptr(red[0]), ptr(red[1]), ptr(aux[2][off:]), ptr(aux[3][off:]), stream())
             direct = _direct_grad(w) and _direct_grad(g) and _direct_grad(b)
             fold = direct and _sync["world"] == 1
-            if direct and not fold:
-                g.grad.add_(red[1])
-                b.grad.add_(red[0])
             dg, db = (None, None) if direct else (red[1].clone(), red[0].clone())
-            _allreduce_stats(red)
+            _allreduce_stats(red, g.grad if (direct and not fold) else None, b.grad if (direct and not fold) else None)
             call("tsb_bn_bwd_apply", ptr(dy), cs_of(dy), None, 0, ptr(xr), K, ptr(aux[0][off:]), ptr(aux[1][off:]), ptr(g),
                  ptr(red[0]), ptr(red[1]), ctx.count, 1, ptr(draw[:, off:off + Kh]), K, None, 0, npix, Kh,
                  ptr(g.grad) if fold else None, ptr(b.grad) if fold else None, ptr(aux[2][off:]), ptr(aux[3][off:]), stream())
