@@ -309,14 +309,25 @@ def pyramid_pooling_logits(x, sd, prefix, eps, momentum, training, scales=(1, 2,
     return F.conv2d(fm, qw(sd[prefix + ".conv6.2.weight"]), sd[prefix + ".conv6.2.bias"])
 
 
+def _up8(x, data):
+    """pspnet / psanet network.py:46-49: F.interpolate(scale_factor=8, bilinear, align_corners=True). For inputs whose
+    size is not a multiple of 8 (BASELINE.json's 713 / 473 crops; the reference's own 480 is) the x8 map does not match
+    the label, so — identically in this oracle and in the B200 networks — the target is the INPUT size (`size=`), which
+    is the same operation whenever both are defined (align_corners: src = dst·(in-1)/(out-1))."""
+    H, W = data.shape[2:]
+    if x.shape[2] * 8 == H and x.shape[3] * 8 == W:
+        return F.interpolate(x, scale_factor=8, mode="bilinear", align_corners=True)
+    return F.interpolate(x, size=(H, W), mode="bilinear", align_corners=True)
+
+
 def pspnet_loss(data, label, sd, layers=(3, 4, 23, 3), aux_ratio=0.4, ignore_label=-1, eps=1e-5, momentum=0.1, stats=None):
     """PSPNet.forward training branch — pspnet network.py:40-57 (x8 bilinear, log_softmax, CE; loss + 0.4*aux)"""
     blocks = resnet_v1c_d8(data, sd, "backbone", layers, eps, momentum, True, stats)
     psp = pyramid_pooling_logits(blocks[-1], sd, "psp_layer", eps, momentum, True, stats=stats)
     aux = conv_bn_relu(blocks[-2], sd, "aux_layer.0", 1, 1, eps=eps, momentum=momentum, training=True, stats=stats)
     aux = F.conv2d(aux, qw(sd["aux_layer.2.weight"]), sd["aux_layer.2.bias"])
-    psp = F.log_softmax(F.interpolate(psp, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
-    aux = F.log_softmax(F.interpolate(aux, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+    psp = F.log_softmax(_up8(psp, data), dim=1)
+    aux = F.log_softmax(_up8(aux, data), dim=1)
     loss = F.cross_entropy(psp, label, ignore_index=ignore_label)
     return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label), (psp, aux)
 
@@ -437,7 +448,7 @@ def psanet_loss(data, label, sd, layers=(3, 4, 23, 3), aux_ratio=0.4, ignore_lab
     psa = psa_logits(blocks[-1], sd, "psa_layer", eps, momentum, True, stats=stats)
     aux = conv_bn_relu(blocks[-2], sd, "aux_layer.0", 1, 1, eps=eps, momentum=momentum, training=True, stats=stats)
     aux = F.conv2d(aux, qw(sd["aux_layer.2.weight"]), sd["aux_layer.2.bias"])
-    psa = F.log_softmax(F.interpolate(psa, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
-    aux = F.log_softmax(F.interpolate(aux, scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+    psa = F.log_softmax(_up8(psa, data), dim=1)
+    aux = F.log_softmax(_up8(aux, data), dim=1)
     loss = F.cross_entropy(psa, label, ignore_index=ignore_label)
     return loss + aux_ratio * F.cross_entropy(aux, label, ignore_index=ignore_label), (psa, aux)

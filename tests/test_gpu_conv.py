@@ -159,3 +159,76 @@ def test_conv_full_size_linearity(cuda):
     assert torch.equal(ya + yb, yab)  # all partial sums are small integers / 4: exact in fp32
     ref = F.conv2d(a[:2].float(), w.permute(0, 3, 1, 2), None, 1, 1)
     assert torch.equal(ya[:2], ref)
+
+
+# BASELINE.json configs[1] layer shapes (batch 16 @ 1024 x 1024 input): the tile choices that only exist at this size —
+# row tiles, persistent CTAs with resident / streamed / PAIRED weights, the nine-tap wgrad kernel, stride-2 parity views
+FULL_SIZE = [
+    (16, 64, 256, 256, 64, 3, 1, 1, 1),     # layer1 (resident weights, row tiles; nine-tap wgrad, K = 64)
+    (16, 64, 256, 256, 128, 3, 2, 1, 1),    # layer2.0.conv1 (stride 2)
+    (16, 128, 128, 128, 128, 3, 1, 1, 1),   # layer2 (streamed weights, tile pairs)
+    (16, 256, 64, 64, 256, 3, 1, 1, 1),     # layer3
+    (16, 512, 32, 32, 512, 3, 1, 1, 1),     # layer4 (TW = 32, TH = 2 tiles in the nine-tap wgrad)
+    (16, 128, 128, 128, 256, 3, 1, 1, 1),   # aux head 3x3
+    (16, 256, 128, 128, 256, 1, 1, 0, 1),   # FFM 1x1 (flat GEMM)
+    (16, 512, 32, 32, 128, 3, 1, 1, 1),     # ARM 3x3
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE, ids=[str(c) for c in FULL_SIZE])
+def test_conv_full_size_vs_cudnn(cuda, case):
+    """fprop / dgrad / wgrad of the BASELINE-size layers against cuDNN in strict fp32 on the same bf16-rounded operands
+    (computed on the GPU). Tolerance 1e-2 of the output scale (bf16 output rounding; fp32 accumulation both sides)."""
+    from torchseg_b200 import ops
+    N, C, H, W, K, R, stride, pad, dil = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        x = torch.randn(N, C, H, W, device=cuda, generator=g).to(torch.bfloat16)
+        w = (torch.randn(K, C, R, R, device=cuda, generator=g) / (C * R * R) ** 0.5).to(torch.bfloat16)
+        P, Q = ops.conv_out_size(H, R, stride, pad, dil), ops.conv_out_size(W, R, stride, pad, dil)
+        gy = torch.randn(N, K, P, Q, device=cuda, generator=g).to(torch.bfloat16)
+        xr = x.float().requires_grad_(True)
+        wr = w.float().requires_grad_(True)
+        y_ref = F.conv2d(xr, wr, None, stride, pad, dil)
+        y_ref.backward(gy.float())
+        xd = ops.to_nhwc(x)
+        wk = w.float().permute(0, 2, 3, 1).contiguous()
+        wb = torch.empty((K, R, R, C), dtype=torch.bfloat16, device=cuda)
+        wt = torch.empty((C, R, R, K), dtype=torch.bfloat16, device=cuda)
+        ops.call("tsb_pack_weight", ops.ptr(wk), K, R, R, C, ops.ptr(wb), ops.ptr(wt), ops.stream())
+        stats = torch.zeros(2, K, device=cuda)
+        y = ops.conv_fprop(xd, wb, K, R, stride, pad, dil, stats=stats)
+        assert rel_err(y, y_ref) < 1e-2
+        yb = y.float()
+        assert rel_err(stats[0], yb.sum(dim=(0, 2, 3))) < 1e-3 and rel_err(stats[1], (yb * yb).sum(dim=(0, 2, 3))) < 1e-3
+        gyd = ops.to_nhwc(gy)
+        dx = ops.conv_dgrad(gyd, wt, (N, C, H, W), K, R, stride, pad, dil)
+        assert rel_err(dx, xr.grad) < 1e-2
+        dw = torch.zeros((K, R, R, C), dtype=torch.float32, device=cuda)
+        ops.conv_wgrad(xd, gyd, K, R, stride, pad, dil, dw)
+        e = rel_err(dw.permute(0, 3, 1, 2), wr.grad)
+        assert e < 2e-3, "wgrad rel err %g (fp32 accumulation of bf16 products: only the summation order differs)" % e
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_wgrad_taps_matches_row_kernel(cuda):
+    """the nine-tap wgrad kernel (tsb_debug_set key 8) against the row-tile kernel on the same operands, dilation 2"""
+    from torchseg_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    N, C, H, W, K, dil = 4, 128, 60, 60, 192, 2
+    x = ops.to_nhwc(torch.randn(N, C, H, W, device=cuda, generator=g))
+    gy = ops.to_nhwc(torch.randn(N, K, H, W, device=cuda, generator=g))
+    outs = []
+    try:
+        for flag in (1, 0):
+            ops.call("tsb_debug_set", 8, flag)
+            dw = torch.zeros((K, 3, 3, C), dtype=torch.float32, device=cuda)
+            ops.conv_wgrad(x, gy, K, 3, 1, dil, dil, dw)
+            outs.append(dw)
+    finally:
+        ops.call("tsb_debug_set", 8, 1)
+    assert rel_err(outs[0], outs[1]) < 1e-4

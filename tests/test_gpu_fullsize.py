@@ -71,6 +71,24 @@ def test_bisenet_full_size_step_matches_oracle_cuda(cuda):
             v.grad = None
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
+        # the SAME fp32 oracle with bf16 STORAGE emulated (values rounded to bf16 wherever the B200 path stores bf16:
+        # conv weights, raw conv outputs, activations — forward and backward). |fp32 − bf16-storage| is the spread that
+        # the storage policy alone produces at this size; the libtsb step has to sit inside it.
+        torch_ref.set_bf16_emulation(True)
+        try:
+            stats_emu = {}
+            loss_emu, _ = torch_ref.bisenet_r18_loss(x, y, sd, min_kept, stats=stats_emu)
+            loss_emu.backward()
+        finally:
+            torch_ref.set_bf16_emulation(False)
+        loss_emu_v = float(loss_emu)
+        grads_emu = {k: v.grad.detach().cpu() for k, v in sd.items() if v.grad is not None}
+        stats_emu = {k: v.detach().cpu() for k, v in stats_emu.items()}
+        del loss_emu
+        for v in sd.values():
+            v.grad = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
     finally:
         torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
@@ -82,7 +100,7 @@ def test_bisenet_full_size_step_matches_oracle_cuda(cuda):
     loss.backward()
     torch.cuda.synchronize()
     rel = abs(loss.item() - loss_ref_v) / abs(loss_ref_v)
-    print("full-size N=%d: loss %.6f oracle %.6f rel %.2e" % (N, loss.item(), loss_ref_v, rel))
+    print("full-size N=%d: loss %.6f oracle %.6f rel %.2e (bf16-storage oracle %.6f)" % (N, loss.item(), loss_ref_v, rel, loss_emu_v))
     assert rel < 1e-2, (loss.item(), loss_ref_v)
 
     # OHEM: kept count per head (aux0, aux1, main — the order the network calls the criterion in). The whole-step counts
@@ -98,35 +116,49 @@ def test_bisenet_full_size_step_matches_oracle_cuda(cuda):
         if abs(n_kept - kept) > 1e-3 * kept:
             failures.append(("kept", i, n_kept, kept))
 
-    # gradients: business layers tight, whole network aligned
+    # gradients. An untrained batch-stat-BN network with random labels has gradients that are the small residue of
+    # massive cancellation over 16.8 M pixels, and bf16 STORAGE alone moves them: `spread` = |oracle fp32 − the same oracle
+    # with bf16 storage emulated|. The libtsb gradients must be as close to the fp32 oracle as that emulation is (x1.5 +
+    # 2e-2), and closer to the emulation than the emulation is to fp32 wherever the spread is large.
+    def _cos(a, b):
+        a, b = a.reshape(-1), b.reshape(-1)
+        return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
     business = ("spatial_path.", "global_context.", "arms.", "refines.", "heads.", "ffm.")
-    worst, bad, cos_bad = [], [], []
+    rows, bad = [], []
     for n, p in model.named_parameters():
-        a, b = p.grad.float().cpu(), grads_ref[n]
-        e = norm_err(a, b)
-        af, bf = a.reshape(-1), b.reshape(-1)
-        cos = float(torch.dot(af, bf) / (af.norm() * bf.norm()).clamp_min(1e-30))
-        worst.append((e, n))
-        if n.startswith(business) and p.dim() == 4 and e > 2e-2:
-            bad.append((n, round(e, 4)))
-        if cos < 0.95:
-            cos_bad.append((n, round(cos, 4)))
-    worst.sort(reverse=True)
-    print("worst gradient norm_err:", [(n, round(e, 4)) for e, n in worst[:8]])
-    print("business-layer norm_err > 2e-2:", bad[:20])
-    print("cosine < 0.95:", cos_bad[:20])
+        a, b, c = p.grad.float().cpu(), grads_ref[n], grads_emu[n]
+        e_ref, e_emu, spread = norm_err(a, b), norm_err(a, c), norm_err(c, b)
+        rows.append((n, e_ref, e_emu, spread, _cos(a, b), _cos(c, b)))
+        if p.dim() == 4 and e_ref > 1.5 * spread + 2e-2:
+            bad.append((n, round(e_ref, 4), round(spread, 4)))
+    print("%-46s %9s %9s %9s %8s %8s" % ("parameter", "err_fp32", "err_emu", "spread", "cos", "cos_emu"))
+    for r in rows:
+        if r[0].endswith("weight") and (r[0].startswith(business) or "conv" in r[0]):
+            print("%-46s %9.4f %9.4f %9.4f %8.4f %8.4f" % r)
+    worst = sorted(((r[1], r[0]) for r in rows), reverse=True)
+    print("worst gradient norm_err vs fp32:", [(n, round(e, 4)) for e, n in worst[:8]])
+    print("outside 1.5 x spread + 2e-2:", bad[:20])
+    cos_bad = [(r[0], round(r[4], 4), round(r[5], 4)) for r in rows if r[4] < r[5] - 0.05]
+    print("cosine below the emulation's by > 0.05:", cos_bad[:20])
+    # the last classifier (one layer from the loss, nothing to amplify): tight
+    e_cls = [r for r in rows if r[0] == "heads.2.conv_1x1.weight"][0][1]
 
     # BN running statistics (momentum 0.1, unbiased variance)
     msd = model.state_dict()
-    stat_bad = []
+    stat_bad, stat_worst = [], 0.0
     for k, v in stats.items():
-        e = float((msd[k].float().cpu() - v).abs().max() / v.abs().max().clamp_min(1e-6))
-        if e >= 1e-2:
-            stat_bad.append((k, round(e, 4)))
-    print("running statistics off by > 1e-2:", stat_bad[:10])
+        den = v.abs().max().clamp_min(1e-6)
+        e = float((msd[k].float().cpu() - v).abs().max() / den)
+        spread = float((stats_emu[k] - v).abs().max() / den)
+        stat_worst = max(stat_worst, e)
+        if e >= 1e-2 + 1.5 * spread:
+            stat_bad.append((k, round(e, 4), round(spread, 4)))
+    print("running statistics: worst rel err %.4f; outside 1e-2 + 1.5 x spread: %s" % (stat_worst, stat_bad[:10]))
     assert not failures, failures
-    assert not bad, "business-layer gradient norm_err > 2e-2: %s" % bad[:10]
-    assert not cos_bad, "gradient cosine < 0.95: %s" % cos_bad[:10]
+    assert not bad, "gradient farther from the fp32 oracle than 1.5 x the bf16-storage spread + 2e-2: %s" % bad[:10]
+    assert not cos_bad, "gradient direction worse than the bf16-storage emulation's: %s" % cos_bad[:10]
+    assert e_cls < 5e-2, e_cls
     assert not stat_bad, stat_bad[:10]
 
 

@@ -33,10 +33,9 @@ int tsb_ensure_dyn_smem(const void* func, size_t bytes) {
     TSB_CUDA_CALL(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(mu);
     size_t& have = done[std::make_pair(dev, func)];
-    if (bytes > have) {
-        const size_t want = bytes > 48 * 1024 ? (size_t)227 * 1024 : bytes;
-        TSB_CUDA_CALL(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-        have = want;
+    if (bytes > have) {   // monotonic: exactly what is asked for (static + dynamic shared memory must fit 227 KB)
+        TSB_CUDA_CALL(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
     }
     return TSB_OK;
 }

@@ -151,17 +151,19 @@ class BiSeNetHead(nn.Module):
     def forward(self, x):
         lo = self.lowres_logits(x)
         if self.scale > 1:
-            return _UpsampleLogitsFn.apply(lo, self.scale)
+            return _UpsampleLogitsFn.apply(lo, lo.shape[2] * self.scale, lo.shape[3] * self.scale)
         return lo
 
 
 class _UpsampleLogitsFn(torch.autograd.Function):
-    """reference-boundary form of the head tail: NCHW fp32 [N,C,H*s,W*s] logits (network.py:164-166)"""
+    """reference-boundary form of the head tail: NCHW fp32 [N,C,H,W] logits, bilinear align_corners=True to an explicit
+    output size (network.py:164-166 use scale_factor; with align_corners the source coordinate is (in-1)/(out-1)·dst
+    either way, so size = in·scale is the same op — and sizes like 713 / 473 that are not a multiple of 8 work too)"""
 
     @staticmethod
-    def forward(ctx, lo, scale):
+    def forward(ctx, lo, H, W):
         N, C, h, w = lo.shape
-        H, W = h * scale, w * scale
+        H, W = int(H), int(W)
         out = torch.empty((N, C, H, W), dtype=torch.float32, device=lo.device)
         ops.call("tsb_bilinear_fwd_nhwc_to_nchw", ops.ptr(lo), ops._lib.dt(lo), ops.cs_of(lo), ops.ptr(out), N, C, h, w,
                  H, W, ops.stream())
@@ -178,4 +180,4 @@ class _UpsampleLogitsFn(torch.autograd.Function):
         d = ops.nhwc_zeros(N, Cp, h, w, dtype=torch.float32, device=g.device, cs=max(cs, Cp))
         ops.call("tsb_bilinear_bwd", ops.ptr(gp), ops.F32, Cp, ops.ptr(d), ops.F32, ops.cs_of(d), N, Cp, h, w, H, W, 0,
                  ops.stream())
-        return d[:, :C], None
+        return d[:, :C], None, None

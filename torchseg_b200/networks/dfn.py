@@ -139,7 +139,7 @@ class DFN(nn.Module):
                 raise ValueError("DFN: label size must be scale x the head resolution")
             li = self._smooth_loss(lo, label)
             if li is None:
-                li = self.criterion(_UpsampleLogitsFn.apply(lo, head.scale), label)
+                li = self.criterion(_UpsampleLogitsFn.apply(lo, lo.shape[2] * head.scale, lo.shape[3] * head.scale), label)
             loss = li if loss is None else loss + li
         aux_loss = None
         for fm, head in zip(border, self.border_heads):
@@ -166,5 +166,5 @@ class DFNHead(nn.Module):
     def forward(self, x):
         lo = self.lowres_logits(x)
         if self.scale > 1:
-            return _UpsampleLogitsFn.apply(lo, self.scale)
+            return _UpsampleLogitsFn.apply(lo, lo.shape[2] * self.scale, lo.shape[3] * self.scale)
         return lo

@@ -70,11 +70,14 @@ class PSPNet(nn.Module):
 
     def forward(self, data, label=None):
         blocks = self.backbone(data)
+        # network.py:46-49 upsample by scale_factor=8, which only reproduces the input size when it is a multiple of 8
+        # (480); `size=` semantics — identical numbers for those sizes — also admit the 713 / 473 crops of BASELINE.json
+        H, W = int(data.shape[2]), int(data.shape[3])
         psp_lo = self.psp_layer(blocks[-1])
-        psp_fm = _UpsampleLogitsFn.apply(psp_lo, 8)            # network.py:46-47
+        psp_fm = _UpsampleLogitsFn.apply(psp_lo, H, W)            # network.py:46-47
         if label is None:
             return torch.log_softmax(psp_fm, dim=1)
-        aux_fm = _UpsampleLogitsFn.apply(self._aux_logits(blocks[-2]), 8)
+        aux_fm = _UpsampleLogitsFn.apply(self._aux_logits(blocks[-2]), H, W)
         ign = _ignore_index_of(self.criterion)
         loss = ops.OhemCEFn.apply(psp_fm, label, ign, 1.0, 0, None)
         aux_loss = ops.OhemCEFn.apply(aux_fm, label, ign, 1.0, 0, None)
