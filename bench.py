@@ -328,8 +328,9 @@ def main():
                     help="bisenet = BASELINE configs[1] (the metric); pspnet / dfn = secondary lines (SURVEY C3 / C4)")
     ap.add_argument("--size", type=int, default=0, help="input size override (pspnet default 480, the reference shape)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true",
-                    help="time the step as ONE CUDA graph replay (engine.graph.GraphedTrainStep); default = eager launches")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="single GPU: time eager launches only (default: the step is ONE CUDA graph replay, "
+                         "engine.graph.GraphedTrainStep; the eager time is reported beside it)")
     ap.add_argument("--default-stream", action="store_true",
                     help="run on the legacy default stream (default: a non-blocking side stream, which whole-step graph capture needs)")
     args = ap.parse_args()
@@ -398,8 +399,8 @@ def main():
 
     it = 0
     for _ in range(warmup):
-        loss = train_step(model, ddp, opt, lr_policy, it, *dev_batch)
-        it += 1
+        train_step(model, ddp, opt, lr_policy, it, *dev_batch)   # (no reference to the loss is kept: a live autograd graph
+        it += 1                                                    # of an eager step invalidates a later whole-step capture)
 
     def timed_eager(nsteps):
         nonlocal it

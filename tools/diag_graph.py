@@ -7,13 +7,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    # name: (batch, size, eager steps before, capture_error_mode, side stream for everything)
-    "fresh_b16": (16, 1024, 0, "global", True),
+    # name: (batch, size, eager steps before, capture_error_mode, side stream for everything[, extras])
     "eager3_b16": (16, 1024, 3, "global", True),
-    "eager3_b16_threadlocal": (16, 1024, 3, "thread_local", True),
-    "eager3_b16_relaxed": (16, 1024, 3, "relaxed", True),
-    "eager3_b4": (4, 1024, 3, "global", True),
-    "eager3_b16_512": (16, 512, 3, "global", True),
+    "eager3_b16_pinned": (16, 1024, 3, "global", True, "pinned"),
+    "eager3_b16_loss_alive": (16, 1024, 3, "global", True, "loss"),
+    "eager3_b16_nosync": (16, 1024, 3, "global", True, "nosync"),
+    "eager3_b16_all": (16, 1024, 3, "global", True, "pinned,loss,nosync"),
 }
 
 
@@ -21,7 +20,8 @@ def one(name):
     import torch
     import bench
     from torchseg_b200.engine.graph import GraphedTrainStep
-    B, size, eager, mode, side = VARIANTS[name]
+    B, size, eager, mode, side = VARIANTS[name][:5]
+    extras = VARIANTS[name][5].split(",") if len(VARIANTS[name]) > 5 else []
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     if side:
@@ -29,13 +29,17 @@ def one(name):
     bench.BATCH_PER_GPU = B
     bench.H = bench.W = size
     model, ddp, opt, lrp = bench.build_b200(dev, 1)
-    batch = tuple(t.to(dev) for t in bench.synth_batch(B, size, size, 100))
+    host = bench.synth_batch(B, size, size, 100, pin="pinned" in extras)
+    batch = tuple(t.to(dev) for t in host)
     for it in range(eager):
-        bench.train_step(model, ddp, opt, lrp, it, *batch)
-    torch.cuda.synchronize()
+        loss = bench.train_step(model, ddp, opt, lrp, it, *batch)
+        if "loss" not in extras:
+            del loss
+    if "nosync" not in extras:
+        torch.cuda.synchronize()
     g = GraphedTrainStep(model, opt, batch, warmup=2, capture_error_mode=mode)
     if g.graph is None:
-        print("RESULT %s FAIL %s" % (name, (g.error or "").split("\n")[0][:160]))
+        print("RESULT %s FAIL %s" % (name, (g.error or "").replace("\n", " | ")[-700:]))
         return
     for _ in range(3):
         loss = g(*batch)

@@ -12,19 +12,21 @@ Usage:
 If capture is impossible (non-CUDA device, an op that cannot be captured) the object runs eager steps and keeps the
 reason in `.error`.
 
-Status: EXPERIMENTAL. Verified on B200: capture + replay follow the eager trajectory (tests/test_gpu_bisenet.py::
-test_graphed_train_step_matches_eager; tools/diag_graph*.py at the bench size: 329 launches per graph), but in the full
-bench.py flow the capture was intermittently invalidated (cudaErrorStreamCaptureInvalidated) by a call not yet
-identified, and a failed capture leaves the eager step ~50 % slower and the process-wide CUDA RNG in capture mode — so
-bench.py keeps eager launches by default (`--graph` opts in) and the GPU test only runs with TSB_TEST_GRAPH=1.
-What the B200 runs showed (tools/diag_graph*.py, tests): captures preceded by warm-up steps on a SIDE stream succeeded
-(first version of the test, diag_graph2 VAR b), captures preceded only by default-stream steps failed (bench flow, the
-test with a hand-written default-stream warm-up) — consistent with PyTorch's documented requirement that the warm-up
-run on a side stream (autograd's leaf-gradient streams must not be the legacy default stream, whose implicit use inside
-a global-mode capture invalidates it); the side-stream warm-up is therefore the default again, with `warmup >= 1`
-required. Ruled out on hardware: cyclic GC during capture (now collected before / disabled during the capture anyway)
-and the pinned-host → device hyper-parameter copy inside the graph (removed: hyper-parameters live in a device tensor
-refreshed by an eager copy before each replay)."""
+Requirements (verified on B200, tools/diag_graph.py — each variant in its own process):
+  * everything runs on ONE non-default stream (`torch.cuda.set_stream(torch.cuda.Stream())` at program start): work that
+    touches the legacy default stream during a capture invalidates it;
+  * NO autograd graph of an earlier eager step may be alive when the object is constructed — e.g. a `loss` tensor still
+    referenced by the training loop (keep `loss.item()` / `loss.detach()` instead). A live graph keeps the parameters'
+    AccumulateGrad nodes alive, and those are bound to the stream they were created on; replayed inside the capture
+    they pull that stream into the capture and it is never joined again (cudaErrorStreamCaptureInvalidated at
+    capture_end — this, not a kernel or an allocator call, was the "intermittent" failure of round 1: bench.py kept
+    the last warm-up loss in a local variable). With that reference dropped every variant captures: fresh process,
+    after eager steps, pinned inputs, global / thread_local / relaxed capture modes, batch 4..16, 512..1024 pixels;
+  * the first optimiser step needs no special case (the momentum buffer starts at exact zeros), so nothing
+    step-dependent is baked into the graph; hyper-parameters live in a device tensor refreshed before each replay.
+Measured: BiSeNet-R18, 16 x 1024 x 1024: 371 launches per graph, 17.8 ms per replay against 19.6 ms of eager launches.
+A failed capture leaves the process-wide CUDA RNG in capture mode and the eager step slower; the object then runs
+eager steps and keeps the reason (with the Python frames) in `.error`."""
 import torch
 
 
@@ -75,7 +77,10 @@ class GraphedTrainStep(object):
             self.launches_per_step = _lib.launch_count() - n0
             self.graph = g
         except Exception as e:  # noqa: BLE001 — fall back to eager steps, keep the reason
-            self.error = "%s: %s" % (type(e).__name__, e)
+            import traceback
+            tb = traceback.extract_tb(e.__traceback__)
+            where = " <- ".join("%s:%d %s" % (f.filename.split("/")[-1], f.lineno, f.name) for f in reversed(tb[-6:]))
+            self.error = "%s: %s [at %s]" % (type(e).__name__, e, where)
             self.graph = None
             try:                 # best effort: release the half-built graph (its RNG registration, its memory pool)
                 g.reset()
