@@ -417,15 +417,18 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1)), clk_, _lib.launch_count() - n0, loss_
 
     # ---------------- timed region 1 (`value`), CLEAN: no event instrumentation, inputs resident in HBM.
-    # Single GPU: the whole step (zero_grad → forward → backward → fused SGD) is ONE CUDA graph replay
-    # (torchseg_b200.engine.graph.GraphedTrainStep) unless --no-graph / capture is unavailable; multi-GPU: eager launches
-    # (the DDP side-stream all-reduce is not captured).
+    # The whole step (zero_grad → forward → backward → [bucketed NCCL gradient all-reduce on the side stream, NVLink SyncBN
+    # exchanges] → fused SGD) is ONE CUDA graph replay (torchseg_b200.engine.graph.GraphedTrainStep) unless --no-graph /
+    # capture is unavailable; the eager-launch time of the same step is measured and reported beside it.
     gstep = None
-    if world == 1 and args.graph:
+    if args.graph and (world == 1 or os.environ.get("TSB_BENCH_GRAPH_MULTI", "1") != "0"):
         from torchseg_b200.engine.graph import GraphedTrainStep
         set_lr(it)
-        gstep = GraphedTrainStep(model, opt, dev_batch, warmup=2)
-        if gstep.graph is None:
+        gstep = GraphedTrainStep(model, opt, dev_batch, warmup=2, ddp=ddp)
+        ok = torch.tensor([1.0 if gstep.graph is not None else 0.0], device=device)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # all ranks replay, or none does
+        if float(ok.item()) < 1.0:
             sys.stderr.write("bench: CUDA graph capture unavailable (%s); eager step timed instead\n" % gstep.error)
             gstep = None
     ms_eager, clk_eager, launches_eager, loss = timed_eager(args.steps)

@@ -294,16 +294,18 @@ int tsb_sigmoid_focal_fwd_bwd(const void* pred, int dtype, const int64_t* target
  * Device-initiated all-reduce of small fp32 vectors over NVLink peer memory — the SyncBatchNorm statistics exchange
  * (replaces the per-layer all-reduce inside apex.parallel.SyncBatchNorm, model/bisenet/cityscapes.bisenet.R18/
  * train.py:54-55). The caller owns ONE symmetric buffer per rank of tsb_p2p_buffer_bytes() bytes, zero-filled before
- * the first exchange, and passes the peer-mapped base address of every rank's buffer (host array `peer_bases[world]`).
- * `seq` = 1, 2, 3, ... must be the same on all ranks for the same exchange. vals[n] (n % 4 == 0, n <= slot_floats) is
+ * the first exchange ({value, sequence} pairs: no fences, no flag resets), and passes the peer-mapped base address of every rank's buffer (host array `peer_bases[world]`).
+ * `seq` = 1, 2, 3, ... must be the same on all ranks for the same exchange; alternatively `seq_dev` points at a device
+ * counter (zero-initialised, private to this buffer) that the kernel pre-increments — the form a captured CUDA graph can
+ * replay. vals[n] (n % 4 == 0, n <= slot_floats) is
  * replaced by the sum over ranks (rank order: identical bits everywhere). Optional acc_hi/acc_lo[n/2]: the LOCAL
  * halves are accumulated first (acc_lo += vals[0:n/2], acc_hi += vals[n/2:n]) — dbeta / dgamma of the BN backward.
  * ============================================================================================== */
 #define TSB_P2P_MAX_WORLD 16
 size_t tsb_p2p_buffer_bytes(int world, int nslots, int slot_floats);
 int tsb_p2p_allreduce_sum(float* vals, int n, const unsigned long long* peer_bases, int rank, int world,
-                          unsigned int seq, int nslots, int slot_floats, float* acc_hi, float* acc_lo,
-                          tsb_stream_t stream);
+                          unsigned int seq, unsigned int* seq_dev, int nslots, int slot_floats, float* acc_hi,
+                          float* acc_lo, tsb_stream_t stream);
 
 #ifdef __cplusplus
 }

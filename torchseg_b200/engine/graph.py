@@ -2,7 +2,7 @@
 
 The step of /root/reference/model/bisenet/cityscapes.bisenet.R18/train.py:116-142 is ~400 kernel launches of 5-200 us
 each; captured once, a replay removes the per-launch CPU work (Python autograd, ctypes, tensor-map encoding) and the
-inter-kernel launch gaps. Single process / single GPU only (the DDP side-stream all-reduce is not captured).
+inter-kernel launch gaps. One process per GPU; with `ddp=` the gradient all-reduce and the SyncBN exchanges are part of the graph.
 
 Usage:
     step = GraphedTrainStep(model, optimizer, example_inputs)     # runs `warmup` eager steps, then captures
@@ -32,9 +32,17 @@ import torch
 
 class GraphedTrainStep(object):
     def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True, side_stream_warmup=True,
-                 capture_error_mode="global"):
+                 capture_error_mode=None, ddp=None):
+        """ddp: the apex.parallel.DistributedDataParallel shim wrapping `model` (multi-GPU): its bucketed NCCL all-reduce
+        on the side stream (fork / join inside the capture) and the NVLink SyncBN exchanges (device-resident sequence
+        counter) are captured too. Every rank must construct the object at the same point of its program."""
         self.model = model
+        self.ddp = ddp
         self.opt = optimizer
+        if capture_error_mode is None:
+            # with NCCL in the process its watchdog thread polls events concurrently: only the capturing thread may be
+            # held to the capture rules
+            capture_error_mode = "thread_local" if ddp is not None else "global"
         self.static_inputs = [t.clone() for t in example_inputs]
         self.graph = None
         self.static_loss = None
@@ -93,8 +101,10 @@ class GraphedTrainStep(object):
 
     def _eager(self, *inputs):
         self.opt.zero_grad()
-        loss = self.model(*inputs)
+        loss = (self.ddp or self.model)(*inputs)
         loss.backward()
+        if self.ddp is not None:
+            self.ddp.finish_reduce()
         self.opt.step()
         return loss
 

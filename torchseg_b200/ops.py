@@ -230,14 +230,15 @@ class _PeerExchange(object):
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(ptrs) == world and all(ptrs)
         self.peers = (ctypes.c_ulonglong * world)(*ptrs)
-        self.seq = 0
+        # the exchange counter lives on the device (pre-incremented by every exchange kernel): identical on all ranks
+        # because all ranks issue the same exchanges, and replayable inside a captured CUDA graph
+        self.seq_dev = torch.zeros(1, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group=pg)      # every rank's buffer is zeroed before anybody's first exchange can write into it
 
     def allreduce(self, buf, acc_hi=None, acc_lo=None):
-        self.seq += 1
         call("tsb_p2p_allreduce_sum", ptr(buf), buf.numel(), ctypes.cast(self.peers, ctypes.c_void_p), self.rank, self.world,
-             self.seq & 0xffffffff or 1, self.NSLOTS, self.SLOT_FLOATS, ptr(acc_hi), ptr(acc_lo), stream())
+             0, ptr(self.seq_dev), self.NSLOTS, self.SLOT_FLOATS, ptr(acc_hi), ptr(acc_lo), stream())
 
 
 def _peer_exchange(device):
