@@ -64,6 +64,13 @@ class DistributedDataParallel(nn.Module):
                     break
         self._comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._pending = False
+        # overlap=True: buckets are reduced on the side stream while backward continues (eager steps). overlap=False: ONE
+        # all-reduce of the whole flat buffer on the compute stream in finish_reduce() — the form used inside a captured
+        # whole-step graph, where every inter-GPU kernel (SyncBN exchanges, this all-reduce) must sit on a single chain:
+        # two independent peer-synchronising kernels in flight need guaranteed concurrency, which graph branches do not
+        # give (a rank that schedules them in the other order deadlocks the pair). The 54 MB (R18) all-reduce costs
+        # ~0.2 ms un-overlapped.
+        self.overlap = True
         if self.world_size > 1:
             ops.set_sync_group(None, self.world_size)
             with torch.no_grad():  # rank 0's parameters win, like the DDP constructor broadcast
@@ -86,6 +93,9 @@ class DistributedDataParallel(nn.Module):
                 view = torch.as_strided(self.flat_grad, param.shape, param.stride(), lo)
                 view.copy_(param.grad)
                 param.grad = view
+            if not self.overlap:
+                self._pending = True
+                return
             b = self._buckets[self._bucket_of[idx]]
             b[3] += 1
             if b[3] == b[2]:
@@ -107,7 +117,10 @@ class DistributedDataParallel(nn.Module):
 
     def finish_reduce(self):
         """make the compute stream wait for outstanding bucket reductions (call before optimizer.step)"""
-        if self._pending and self._comm_stream is not None:
+        if self.world_size > 1 and not self.overlap:
+            dist.all_reduce(self.flat_grad)
+            self.flat_grad.div_(self.world_size)
+        elif self._pending and self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         self._pending = False
 

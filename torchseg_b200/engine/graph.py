@@ -38,6 +38,8 @@ class GraphedTrainStep(object):
         counter) are captured too. Every rank must construct the object at the same point of its program."""
         self.model = model
         self.ddp = ddp
+        if ddp is not None:
+            ddp.overlap = False      # single chain of inter-GPU kernels inside the graph (see the DDP shim)
         self.opt = optimizer
         if capture_error_mode is None:
             # with NCCL in the process its watchdog thread polls events concurrently: only the capturing thread may be
