@@ -496,6 +496,9 @@ def main():
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     assert bool(torch.isfinite(loss_host).all()), "non-finite loss in the e2e region"
 
+    step_launch = "one CUDA graph replay per step (GraphedTrainStep)" if gstep is not None else "eager launches"
+    if gstep is not None:
+        gstep.release()    # a live graph that captured NCCL kernels blocks the communicator teardown
     if world > 1:      # all collective work is done: ranks > 0 leave, rank 0 reports (no rank spins in a barrier)
         dist.barrier()
         dist.destroy_process_group()
@@ -526,7 +529,8 @@ def main():
                        "sync_bn": world > 1, "optimizer": "fused flat SGD (momentum 0.9, poly LR, reference wd / lr groups)",
                        "l2_policy": "inputs larger than L2 (activations >> 126 MB per step), no explicit flush",
                        "final_loss": final_loss,
-                       "step_launch": ("one CUDA graph replay per step (GraphedTrainStep)" if gstep is not None else "eager launches"),
+                       "step_launch": step_launch,
+                       "sync_bn_exchange": (None if world == 1 else ("NVLink peer-memory kernel (tsb_p2p_allreduce_sum)" if ops._sync.get("p2p") is not None else "NCCL all-reduce per layer")),
                        "eager_ms_per_step": ms_eager / args.steps,
                        "step_conv_gflop_per_img": STEP_GFLOP_PER_IMG,
                        "frac_of_conv_flop_roofline": value / world * STEP_GFLOP_PER_IMG / 1e3 / peaks["tflops"]},

@@ -36,4 +36,5 @@ if g.graph is not None:
     flat = opt.flat_param.clone(); other = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(other, flat)
     say("ranks identical after replays: %s" % all(torch.equal(o, other[0]) for o in other))
+g.release()
 dist.barrier(); dist.destroy_process_group(); say("done")

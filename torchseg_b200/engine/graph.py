@@ -101,6 +101,20 @@ class GraphedTrainStep(object):
             except Exception:    # noqa: BLE001
                 pass
 
+    def release(self):
+        """destroy the captured graph (and its memory pool). REQUIRED before dist.destroy_process_group() when the graph
+        contains NCCL kernels: NCCL's communicator teardown waits for every graph that captured it (observed: a hang in
+        destroy_process_group with a live graph)."""
+        g, self.graph = self.graph, None
+        self.static_loss = None
+        if g is not None:
+            torch.cuda.synchronize()
+            g.reset()
+            del g
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+
     def _eager(self, *inputs):
         self.opt.zero_grad()
         loss = (self.ddp or self.model)(*inputs)
