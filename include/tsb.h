@@ -307,6 +307,20 @@ int tsb_p2p_allreduce_sum(float* vals, int n, const unsigned long long* peer_bas
                           unsigned int seq, unsigned int* seq_dev, int nslots, int slot_floats, float* acc_hi,
                           float* acc_lo, tsb_stream_t stream);
 
+/* ================================================================================================
+ * Training-time input pipeline — replaces TrainPre.__call__, model/bisenet/cityscapes.bisenet.R18/
+ * dataloader.py:16-33 (random_mirror, random_scale = cv2.resize INTER_LINEAR / INTER_NEAREST, normalize,
+ * random_crop_pad_to_shape, transpose; furnace/utils/img_utils.py:24-78,118-125,140-145,181-187), one fused pass from the
+ * decoded uint8 frames to the fp32 [n,3,crop_h,crop_w] batch and the int64 [n,crop_h,crop_w] labels. Bit-exact with the
+ * cv2 path (fixed-point 8-bit INTER_LINEAR). The random draws are the caller's (host).
+ * samples_dev: device array of n rows x 10 int64: {img ptr (uint8 [H,W,3]), gt ptr (uint8 [H,W]), H, W, flip (0/1),
+ * sh, sw (size after random_scale), pos_h, pos_w (crop origin in the scaled image), 0}. reverse_channels: the frame is
+ * BGR as decoded and the output planes are RGB (BaseDataset.py:45). lut: [3][256] normalised values per output plane.
+ * ============================================================================================== */
+int tsb_train_preprocess(const long long* samples_dev, int n, int crop_h, int crop_w, int reverse_channels,
+                         const float* lut, float img_pad, int gt_pad, float* out_img, long long* out_gt,
+                         tsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

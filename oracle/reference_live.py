@@ -88,3 +88,31 @@ def load_evaluator():
     if not hasattr(collections, "Iterable"):
         collections.Iterable = collections.abc.Iterable
     return importlib.import_module("engine.evaluator")
+
+
+def load_train_pre(rel_dir, **cfg):
+    """import model/<rel_dir>/dataloader.py (TrainPre) with a stand-in `config` (train_scale_array, image_height,
+    image_width, ...) and the collections.Iterable alias img_utils.py:9 needs under Python >= 3.10"""
+    import collections
+    import collections.abc
+    _ensure_base()
+    if not hasattr(collections, "Iterable"):
+        collections.Iterable = collections.abc.Iterable
+    c = _Cfg(**cfg)
+    cmod = types.ModuleType("config")
+    cmod.config = c
+    saved = sys.modules.get("config")
+    sys.modules["config"] = cmod
+    try:
+        path = os.path.join(REF, "model", rel_dir, "dataloader.py")
+        name = "refdl_" + rel_dir.replace("/", "_").replace(".", "_")
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is not None:
+            sys.modules["config"] = saved
+        else:
+            del sys.modules["config"]
+    mod.config = c      # TrainPre.__call__ reads the module-level name at call time
+    return mod

@@ -77,3 +77,14 @@ def psanet_case(N=1, HW=480, seed=304, classes=150):
     x = torch.randn(N, 3, HW, HW, generator=g)
     y = torch.randint(-1, classes, (N, HW, HW), generator=g, dtype=torch.int64)
     return x, y, seed
+
+
+def pipeline_case(H=100, W=160, crop=(96, 128), seed=1):
+    """a decoded uint8 BGR frame + label map, the BiSeNet scale array and normalisation constants (config.py:61-62,86)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    gt = rng.integers(0, 20, (H, W), dtype=np.uint8)
+    gt[rng.random((H, W)) < 0.05] = 255
+    return (bgr, gt, crop, [0.75, 1, 1.25, 1.5, 1.75, 2.0], np.array([0.485, 0.456, 0.406]),
+            np.array([0.229, 0.224, 0.225]))

@@ -155,6 +155,25 @@ def main():
                                                    "psa_layer.distribute_reduction.conv.weight",
                                                    "psa_layer.proj.conv.weight", "psa_layer.conv6.2.weight")}}
 
+    # input pipeline: the LIVE TrainPre (bisenet dataloader.py:11-33) on a seeded synthetic frame, one entry per RNG seed
+    import random
+    import numpy as np
+    from golden_cases import pipeline_case
+    bgr, gt, crop, scales, mean, std = pipeline_case()
+    dl = rl.load_train_pre('bisenet/cityscapes.bisenet.R18', train_scale_array=scales, image_height=crop[0],
+                           image_width=crop[1], image_mean=mean, image_std=std)
+    pre = dl.TrainPre(mean, std)
+    pipe = {}
+    for seed in range(16):
+        random.seed(seed)
+        p_img, p_gt, _ = pre(bgr[:, :, ::-1], gt)                      # BaseDataset.py:45 reverses the channels first
+        a = torch.from_numpy(np.ascontiguousarray(p_img)).float()       # BaseDataset.py:50-51
+        b = torch.from_numpy(np.ascontiguousarray(p_gt)).long()
+        pipe[str(seed)] = {"data_sha256": sha(a), "label_sha256": sha(b), "shape": list(a.shape),
+                           "data_sum": float(a.double().sum()), "label_sum": int(b.sum())}
+    with open(os.path.join(OUT, "data_pipeline.json"), "w") as f:
+        json.dump({"cv2": __import__("cv2").__version__, "cases": pipe}, f, indent=1, sort_keys=True)
+
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "reference_outputs.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
