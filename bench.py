@@ -279,6 +279,68 @@ def gpu_reference_steps(device, n, h, w, steps, warmup, mode):
         torch.cuda.empty_cache()
 
 
+def run_eval_bench(args, device):
+    """SURVEY §8 f2: evaluator forward throughput — BiSeNet-R18 in eval mode (main head, x8 bilinear, log_softmax;
+    network.py:110-111) on whole Cityscapes frames (1024 x 2048), the libtsb path with the BatchNorm folded into the conv
+    operands vs the same path un-folded vs the oracle restatement of the reference eval forward on cuDNN (fp32 and bf16
+    autocast + channels_last). Not part of the driver's contract: a secondary line (profiles/)."""
+    import torch.nn.functional as F
+    import torchseg_b200
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.seg_opr import seg_oprs
+    from torchseg_b200.utils.init_func import init_weight
+    from oracle import torch_ref
+    n, h, w = args.batch, 1024, 2048
+    torch.manual_seed(12345)
+    model = BiSeNet(NUM_CLASSES, False, None, None, torch.nn.BatchNorm2d)
+    init_weight(model.business_layer, torch.nn.init.kaiming_normal_, torch.nn.BatchNorm2d, 1e-5, 0.1, mode='fan_in',
+                nonlinearity='relu')
+    sd = {k: v.detach().clone().to(device) for k, v in model.state_dict().items()}
+    model.to(device)
+    torchseg_b200.prepare_model(model)
+    model.eval()
+    x = torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(3)).to(device)
+
+    def timeit(fn, steps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return dict(value=n / (ms / 1000.0), unit="images/sec", ms_per_batch=ms)
+
+    res = {}
+    with torch.no_grad():
+        for fold in (True, False):
+            seg_oprs.EVAL_FOLD_BN = fold
+            res["folded_bn" if fold else "unfolded_bn"] = timeit(lambda: model(x), args.steps)
+        seg_oprs.EVAL_FOLD_BN = True
+
+        def ref(mode):
+            def f():
+                xx = x.contiguous(memory_format=torch.channels_last) if mode == "bf16" else x
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+                    lo, _ = torch_ref.bisenet_r18_forward(xx, sd, training=False)
+                return F.log_softmax(F.interpolate(lo[2].float(), scale_factor=8, mode="bilinear", align_corners=True), dim=1)
+            return f
+        torch.backends.cudnn.benchmark = True
+        for mode in ("fp32", "bf16"):
+            torch.backends.cudnn.allow_tf32 = mode != "fp32"
+            res["reference_cudnn_" + mode] = timeit(ref(mode), max(3, args.steps // 2))
+    best_ref = max(res["reference_cudnn_fp32"]["value"], res["reference_cudnn_bf16"]["value"])
+    line = {"metric": "images/sec evaluator forward (1024x2048, 19-class, eval-mode BiSeNet-R18)", "value": res["folded_bn"]["value"],
+            "unit": "images/sec", "n_gpus": 1, "steps": args.steps, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BiSeNet-R18 eval forward incl. x8 upsample + log_softmax, whole 1024x2048 frames", "batch": n},
+            "detail": res, "speedup_folding": res["folded_bn"]["value"] / res["unfolded_bn"]["value"],
+            "speedup_vs_best_reference_gpu": res["folded_bn"]["value"] / best_ref}
+    print(json.dumps(line))
+
+
 def pick_threads():
     """torch CPU ops do not scale to every hardware thread of a big host: calibrate on a tiny step and use the
     fastest of {all, 64, 32, 16} threads (reported as `cores`)."""
@@ -331,6 +393,7 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="single GPU: time eager launches only (default: the step is ONE CUDA graph replay, "
                          "engine.graph.GraphedTrainStep; the eager time is reported beside it)")
+    ap.add_argument("--eval", action="store_true", help="secondary line: evaluator forward throughput (BN folding), 1 GPU")
     ap.add_argument("--default-stream", action="store_true",
                     help="run on the legacy default stream (default: a non-blocking side stream, which whole-step graph capture needs)")
     args = ap.parse_args()
@@ -348,6 +411,10 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", init_method="env://", device_id=device)
+    if args.eval:
+        if args.batch == BATCH_PER_GPU:
+            args.batch = 4
+        return run_eval_bench(args, device)
     if not args.default_stream:
         # everything (warm-up, timed regions, autograd's accumulation streams) lives on ONE non-default stream: a stream
         # capture is invalidated by any work that touches the legacy default stream

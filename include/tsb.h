@@ -246,6 +246,11 @@ typedef struct {
  * accumulated into sum[K], sumsq[K] (fp32, caller zeroes) — the BN-statistics epilogue. */
 int tsb_conv2d_fprop(const tsb_conv_shape* s, const void* x, int xcs, const void* w, const float* bias, void* y,
                      int ydtype, int ycs, float* sum, float* sumsq, tsb_stream_t stream);
+/* inference form with the BatchNorm FOLDED into the weights (evaluator path, furnace/engine/evaluator.py:255-275 runs the
+ * network in eval mode): y = relu?(conv(x, w_folded) + bias (+ res)) in the conv epilogue — no raw tensor, no BN pass.
+ * res (optional, bf16) must be laid out exactly like y (rescs == ycs): the shortcut of a residual block. */
+int tsb_conv2d_fprop_fused(const tsb_conv_shape* s, const void* x, int xcs, const void* w, const float* bias,
+                           const void* res, int rescs, int relu, void* y, int ydtype, int ycs, tsb_stream_t stream);
 /* dgrad: dx = conv_transpose(dy, w). wt is the flipped-transposed pack. dx bf16 (channel stride dxcs).
  * If accumulate != 0, dx += result (residual / multi-consumer gradient accumulation in the epilogue). */
 int tsb_conv2d_dgrad(const tsb_conv_shape* s, const void* dy, int dycs, const void* wt, void* dx, int dxcs,
@@ -257,6 +262,8 @@ int tsb_conv2d_wgrad(const tsb_conv_shape* s, const void* x, int xcs, const void
  * xs2d [N,H/2,W/2+4,16] bf16, wp [K,4,4,16] bf16 → y [N,H/2,W/2,K]. */
 int tsb_conv_stem_fprop(const void* xs2d, int N, int H, int W, const void* wp, int K, void* y, int ycs, float* sum,
                         float* sumsq, tsb_stream_t stream);
+int tsb_conv_stem_fprop_fused(const void* xs2d, int N, int H, int W, const void* wp, int K, const float* bias, int relu,
+                              void* y, int ycs, tsb_stream_t stream);
 int tsb_conv_stem_wgrad(const void* xs2d, int N, int H, int W, const void* dy, int dycs, int K, float* dwp,
                         tsb_stream_t stream);
 /* column sums: db[k] += Σ_pixels dy[pix,k] (bias gradient of the 1x1 classifier heads) */

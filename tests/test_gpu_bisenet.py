@@ -476,3 +476,48 @@ def test_bisenet_eval_forward_matches_oracle(cuda):
     assert norm_err(out, ref) < 2e-2, norm_err(out, ref)
     assert (out.argmax(1).cpu() == ref.argmax(1)).float().mean() > 0.97
     assert torch.equal(model.context_path.bn1.running_mean, rm_before), "eval must not touch the running statistics"
+
+
+def test_bisenet_eval_bn_folding_matches_unfolded(cuda):
+    """evaluator forward with the BatchNorm folded into the conv operands (bias + shortcut + ReLU in the conv epilogue,
+    tsb_conv2d_fprop_fused / tsb_conv_stem_fprop_fused) against the un-folded eval path (raw conv → tsb_bn_apply): same
+    log-probabilities up to the bf16 rounding of the folded weights, far fewer kernel launches, no BN pass"""
+    import torchseg_b200
+    from torchseg_b200 import _lib
+    from torchseg_b200.networks import BiSeNet
+    from torchseg_b200.seg_opr import seg_oprs
+    from torchseg_b200.utils.init_func import init_weight
+    torch.manual_seed(13)
+    model = BiSeNet(19, False, None, None, BN)
+    init_weight(model.business_layer, torch.nn.init.kaiming_normal_, BN, 1e-5, 0.1, mode='fan_in', nonlinearity='relu')
+    g = torch.Generator().manual_seed(14)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, BN):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 1.5 + 0.5)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    model.to(cuda)
+    torchseg_b200.prepare_model(model)
+    model.eval()
+    x = torch.randn(2, 3, 256, 320, generator=g).to(cuda)
+    outs, launches = {}, {}
+    try:
+        for fold in (False, True):
+            seg_oprs.EVAL_FOLD_BN = fold
+            with torch.no_grad():
+                model(x)                                  # warm (packs, fold cache)
+                n0 = _lib.launch_count()
+                outs[fold] = model(x)
+                launches[fold] = _lib.launch_count() - n0
+    finally:
+        seg_oprs.EVAL_FOLD_BN = True
+    assert norm_err(outs[True], outs[False]) < 1e-2, norm_err(outs[True], outs[False])
+    assert (outs[True].argmax(1) == outs[False].argmax(1)).float().mean() > 0.99
+    assert launches[True] <= launches[False] - 40, launches     # ~30 BN layers: finalize + apply launches are gone
+    # parameters change → the folded operands follow (version / optimiser-step keyed cache)
+    with torch.no_grad():
+        model.ffm.conv_1x1.bn.weight.mul_(1.5)
+        changed = model(x)
+    assert norm_err(changed, outs[True]) > 1e-3

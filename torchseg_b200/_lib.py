@@ -63,6 +63,8 @@ _SIGS = {
     "tsb_transpose_pad": [P, I, I, P, I, I, I, I, P],
     "tsb_relu_bwd": [P, I, P, I, P, I, L, I, P],
     "tsb_conv2d_fprop": [P, P, I, P, P, P, I, I, P, P, P],
+    "tsb_conv2d_fprop_fused": [P, P, I, P, P, P, I, I, P, I, I, P],
+    "tsb_conv_stem_fprop_fused": [P, I, I, I, P, I, P, I, P, I, P],
     "tsb_conv2d_dgrad": [P, P, I, P, P, I, I, P],
     "tsb_conv2d_wgrad": [P, P, I, P, I, P, P],
     "tsb_conv_stem_fprop": [P, I, I, I, P, I, P, I, P, P, P],

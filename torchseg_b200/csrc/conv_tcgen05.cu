@@ -399,8 +399,8 @@ int launch_wg(const WgParams& prm, int splits, int co_tiles, int groups, cudaStr
 // =================================================================================================
 // C ABI
 // =================================================================================================
-extern "C" int tsb_conv2d_fprop(const tsb_conv_shape* s, const void* x, int xcs, const void* w, const float* bias,
-                                void* y, int ydtype, int ycs, float* sum, float* sumsq, tsb_stream_t stream) {
+static int fprop_impl(const tsb_conv_shape* s, const void* x, int xcs, const void* w, const float* bias, void* y, int ydtype,
+                      int ycs, float* sum, float* sumsq, const void* res, int relu, tsb_stream_t stream) {
     int rc = check_conv_shape(s, "tsb_conv2d_fprop");
     if (rc) return rc;
     TSB_REQUIRE(x && w && y, "tsb_conv2d_fprop: null pointer");
@@ -465,10 +465,25 @@ extern "C" int tsb_conv2d_fprop(const tsb_conv_shape* s, const void* x, int xcs,
         d.out_n_stride = prm.out_n_stride; d.out_p_stride = prm.out_p_stride; d.out_q_stride = prm.out_q_stride; d.out_base = 0;
         d.k_real = s->K; d.k_store = kst; d.out_f32 = prm.out_f32; d.accumulate = 0;
         d.bias = bias; d.sum = sum; d.sumsq = sumsq; d.out = y;
+        d.relu = relu; d.res = res;
         return convv2::launch(d, st);
     }
+    TSB_REQUIRE(res == nullptr && relu == 0, "tsb_conv2d_fprop_fused: the fused inference epilogue needs the persistent kernel (tsb_debug_set 4)");
     int tiles = prm.tiles_w * prm.tiles_h * N;
     return launch_km_auto(prm, w, s->K, (long long)s->R * s->S * s->C, kst, tiles, st);
+}
+
+extern "C" int tsb_conv2d_fprop(const tsb_conv_shape* s, const void* x, int xcs, const void* w, const float* bias,
+                                void* y, int ydtype, int ycs, float* sum, float* sumsq, tsb_stream_t stream) {
+    return fprop_impl(s, x, xcs, w, bias, y, ydtype, ycs, sum, sumsq, nullptr, 0, stream);
+}
+
+extern "C" int tsb_conv2d_fprop_fused(const tsb_conv_shape* s, const void* x, int xcs, const void* w, const float* bias,
+                                      const void* res, int rescs, int relu, void* y, int ydtype, int ycs,
+                                      tsb_stream_t stream) {
+    TSB_REQUIRE(res == nullptr || (rescs == ycs && ydtype == TSB_BF16 && tsb_aligned16(res)),
+                "tsb_conv2d_fprop_fused: the residual must be a bf16 tensor laid out exactly like the output (rescs == ycs)");
+    return fprop_impl(s, x, xcs, w, bias, y, ydtype, ycs, nullptr, nullptr, res, relu != 0, stream);
 }
 
 extern "C" int tsb_conv2d_dgrad(const tsb_conv_shape* s, const void* dy, int dycs, const void* wt, void* dx, int dxcs,
@@ -656,8 +671,8 @@ int encode_stem_map(CUtensorMap* m, const void* xs2d, int N, int H2, int W2, int
 }
 }  // namespace
 
-extern "C" int tsb_conv_stem_fprop(const void* xs2d, int N, int H, int W, const void* wp, int K, void* y, int ycs,
-                                   float* sum, float* sumsq, tsb_stream_t stream) {
+static int stem_fprop_impl(const void* xs2d, int N, int H, int W, const void* wp, int K, void* y, int ycs, float* sum,
+                           float* sumsq, const float* bias, int relu, tsb_stream_t stream) {
     TSB_REQUIRE(xs2d && wp && y && N > 0 && H > 0 && W > 0 && K > 0, "tsb_conv_stem_fprop: bad args");
     TSB_REQUIRE(H % 2 == 0 && W % 2 == 0 && ycs % 8 == 0 && K % 8 == 0, "tsb_conv_stem_fprop: H,W even; K, ycs multiples of 8");
     TSB_REQUIRE((sum == nullptr) == (sumsq == nullptr), "tsb_conv_stem_fprop: sum and sumsq go together");
@@ -692,10 +707,22 @@ extern "C" int tsb_conv_stem_fprop(const void* xs2d, int N, int H, int W, const 
         d.out_n_stride = prm.out_n_stride; d.out_p_stride = prm.out_p_stride; d.out_q_stride = prm.out_q_stride;
         d.k_real = K; d.k_store = K;
         d.sum = sum; d.sumsq = sumsq; d.out = y;
+        d.bias = bias; d.relu = relu;
         return convv2::launch(d, (cudaStream_t)stream);
     }
+    TSB_REQUIRE(bias == nullptr && relu == 0, "tsb_conv_stem_fprop_fused: the fused inference epilogue needs the persistent kernel");
     int tiles = prm.tiles_w * prm.tiles_h * N;
     return launch_km_auto(prm, wp, K, 256, K, tiles, (cudaStream_t)stream);
+}
+
+extern "C" int tsb_conv_stem_fprop(const void* xs2d, int N, int H, int W, const void* wp, int K, void* y, int ycs,
+                                   float* sum, float* sumsq, tsb_stream_t stream) {
+    return stem_fprop_impl(xs2d, N, H, W, wp, K, y, ycs, sum, sumsq, nullptr, 0, stream);
+}
+
+extern "C" int tsb_conv_stem_fprop_fused(const void* xs2d, int N, int H, int W, const void* wp, int K, const float* bias,
+                                         int relu, void* y, int ycs, tsb_stream_t stream) {
+    return stem_fprop_impl(xs2d, N, H, W, wp, K, y, ycs, nullptr, nullptr, bias, relu != 0, stream);
 }
 
 extern "C" int tsb_conv_stem_wgrad(const void* xs2d, int N, int H, int W, const void* dy, int dycs, int K, float* dwp,

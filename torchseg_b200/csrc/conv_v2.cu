@@ -43,6 +43,8 @@ struct alignas(64) V2Params {
     long long out_n_stride, out_p_stride, out_q_stride, out_base;
     int k_real, k_store, out_f32, accumulate;
     int wide_io;   // every output pixel row is 32-byte aligned → 256-bit epilogue loads / stores
+    int relu;      // inference epilogue: y = max(acc + bias (+ res), 0)
+    const void* res;   // optional bf16 residual with the OUTPUT's addressing (same strides / base), added before the ReLU
     const float* bias;
     float* sum;
     float* sumsq;
@@ -320,6 +322,21 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_v2_kernel(const __grid_cons
 #pragma unroll
                     for (int q = 0; q < 32; ++q)
                         if (col0 + q < p.k_real) v[q] += __ldg(p.bias + col0 + q);
+                }
+                if (p.res != nullptr && valid) {     // folded-BN inference tail of a residual block: + shortcut
+                    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix_off + col0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (col0 + g * 8 < p.k_store) {
+                            float rv[8];
+                            unpack8(*reinterpret_cast<const uint4*>(rp + g * 8), rv);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[g * 8 + q] += rv[q];
+                        }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
                 }
                 if (p.out_f32) {
                     float* o = reinterpret_cast<float*>(p.out) + pix_off + col0;
@@ -702,6 +719,7 @@ int launch(const Desc& d, cudaStream_t st) {
     prm.out_base = d.out_base;
     prm.k_real = d.k_real; prm.k_store = d.k_store; prm.out_f32 = d.out_f32; prm.accumulate = d.accumulate;
     prm.bias = d.bias; prm.sum = d.sum; prm.sumsq = d.sumsq; prm.out = d.out;
+    prm.relu = d.relu; prm.res = d.res;
     prm.use_base_offset = g_use_base_offset;
     {
         const long long es = d.out_f32 ? 4 : 2;

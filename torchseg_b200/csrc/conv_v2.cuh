@@ -29,6 +29,8 @@ struct Desc {
     float* sum;
     float* sumsq;
     void* out;
+    int relu;          // inference epilogue (folded BN): ReLU after bias (+ res)
+    const void* res;   // bf16 residual addressed exactly like `out`
 };
 
 struct WgradDesc {

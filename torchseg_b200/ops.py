@@ -338,6 +338,69 @@ def conv_fprop(x, wb, K, R, stride, pad, dil, bias=None, out_dtype=_BF, out=None
     return out
 
 
+def conv_fprop_fused(x, wb, K, R, stride, pad, dil, bias, res=None, relu=False):
+    """inference conv with the BatchNorm folded into (wb, bias): y = relu?(conv(x) + bias (+ res)) in ONE kernel
+    (tsb_conv2d_fprop_fused) — no raw tensor, no separate normalisation pass"""
+    N, C, H, W = x.shape
+    shp = make_shape(N, H, W, C, K, R, stride, pad, dil)
+    out = nhwc_empty(N, K, shp.P, shp.Q, device=x.device, cs=(K + 7) // 8 * 8)
+    if res is not None and (res.dtype != _BF or res.stride(1) != 1 or cs_of(res) != cs_of(out)):
+        res = to_nhwc(res) if cs_of(out) == K else None
+        assert res is not None, "residual layout must match the output"
+    ev = conv_prof.begin()
+    call("tsb_conv2d_fprop_fused", ctypes.byref(shp), ptr(x), cs_of(x), ptr(wb), ptr(bias), ptr(res),
+         cs_of(res) if res is not None else 0, int(relu), ptr(out), BF16, cs_of(out), stream())
+    conv_prof.end(ev, _conv_flops(shp))
+    return out
+
+
+def conv_stem_fprop_fused(xs2d, wp, K, bias, relu=True):
+    """the 7x7/2 (or 3x3/2) C_in = 3 stem on the space-to-depth image with folded BN + ReLU in the epilogue"""
+    N, _, H2, WP = xs2d.shape
+    H, W = H2 * 2, (WP - 4) * 2
+    out = nhwc_empty(N, K, H2, WP - 4, device=xs2d.device)
+    ev = conv_prof.begin()
+    call("tsb_conv_stem_fprop_fused", ptr(xs2d), N, H, W, ptr(wp), K, ptr(bias), int(relu), ptr(out), K, stream())
+    conv_prof.end(ev, 2.0 * N * H2 * (WP - 4) * K * 147)
+    return out
+
+
+class _FoldCache(object):
+    """eval-mode BatchNorm folded into the conv operands: w' = w · γ/√(σ²+ε) (bf16 KRSC pack), b' = β − μ·γ/√(σ²+ε).
+    One entry per (conv weight, bn) pair, rebuilt when any of the five tensors changes (their versions, plus
+    pack_cache.step because the fused SGD / a graph replay updates parameters without bumping versions)."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, w, bn, stem):
+        key = (id(w), id(bn))
+        ver = (w.data_ptr(), w._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
+               bn.running_var._version, pack_cache.step, bool(stem))
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == ver and hit[3]() is w:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps))
+            bias = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+            wk = (_krsc_ptr(w).float() * scale[:, None, None, None]).contiguous()
+            K, R, S, C = wk.shape
+            if stem:
+                wb = torch.empty((K, 4, 4, 16), dtype=_BF, device=w.device)
+                call("tsb_pack_stem_weight", ptr(wk), K, R, ptr(wb), stream())
+            else:
+                wb = torch.empty((K, R, S, C), dtype=_BF, device=w.device)
+                call("tsb_pack_weight", ptr(wk), K, R, S, C, ptr(wb), None, stream())
+        self.cache[key] = (ver, wb, bias, weakref.ref(w))
+        if len(self.cache) > 1024:
+            for k in [k for k, v in self.cache.items() if v[3]() is None]:
+                del self.cache[k]
+        return wb, bias
+
+
+fold_cache = _FoldCache()
+
+
 def conv_dgrad(dy, wt, xshape, K, R, stride, pad, dil, out=None, accumulate=False):
     N, C, H, W = xshape
     shp = make_shape(N, H, W, C, K, R, stride, pad, dil)

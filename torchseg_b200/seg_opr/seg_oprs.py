@@ -72,6 +72,9 @@ def _ragged(conv, x):
     return conv.in_channels != x.shape[1] or conv.in_channels % 64 != 0
 
 
+EVAL_FOLD_BN = True   # eval mode: fold the BatchNorm into the conv weights, bias (+ residual) + ReLU in the conv epilogue
+
+
 def conv_bn_act(x, conv, bn, relu, residual=None, in_share=None, res_share=None):
     """fused conv → norm_layer(train/eval) → (+residual) → ReLU on the libtsb path.
     in_share / res_share: ops.GradShare of a block-level fork (see BasicBlock.forward)"""
@@ -99,6 +102,13 @@ def conv_bn_act(x, conv, bn, relu, residual=None, in_share=None, res_share=None)
             rm, rv = _pad_vec(rm, Kp), _pad_vec(rv, Kp, 1.0)
     if padded or stem or not bn.training:
         in_share = res_share = None
+    if (not bn.training) and EVAL_FOLD_BN and not padded and not torch.is_grad_enabled():
+        # inference (evaluator.py:255-275): w' = w·γ/σ, b' = β − μ·γ/σ, epilogue = + b' (+ shortcut) → ReLU
+        wb, bias = ops.fold_cache.get(conv.weight, bn, stem)
+        if stem:
+            return ops.conv_stem_fprop_fused(xin, wb, K, bias, relu=bool(relu))
+        return ops.conv_fprop_fused(xin, wb, K, ks, conv.stride[0], conv.padding[0], conv.dilation[0], bias,
+                                    res=residual, relu=bool(relu))
     y = ops.ConvBNActFn.apply(xin, w, gamma, beta, residual, rm, rv,
                               conv.stride[0], conv.padding[0], conv.dilation[0], bool(relu), float(bn.eps),
                               float(momentum), bool(bn.training), stem, in_share, res_share)
