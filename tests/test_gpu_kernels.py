@@ -338,3 +338,68 @@ def test_cuda_prefetcher_delivers_batches_in_order(cuda):
         seen += 1
         del acc
     assert seen == 7
+
+
+@pytest.mark.parametrize("cfg", [(19, 16, False), (21, 8, True), (20, 8, False), (19, 4, True)],
+                         ids=["c19_x16", "c21_x8_weighted", "c20_generic", "c19_x4_weighted"])
+def test_ohem_fused_upsample_variants(cuda, cfg):
+    """exact-class-count band kernels (C = 19 / 21) and the generic fallback (C = 20), scales x4 / x8 / x16, class
+    weights: p bits and kept set vs the C oracle, gradient vs autograd through F.interpolate + the torch restatement"""
+    ops = _ops()
+    from oracle import c_oracle, torch_ref
+    C, s, weighted = cfg
+    N, h, w = 2, 12, 40
+    H, W = h * s, w * s
+    g = torch.Generator().manual_seed(100 + C + s)
+    labels = make_labels(N, H, W, C, 255, g)
+    lo = torch.randn(N, h, w, 32, generator=g) * 2
+    lab_lo = labels[:, ::s, ::s].clamp(max=C - 1)
+    lo[..., :C] += 3 * F.one_hot(lab_lo, C).float()
+    cwt = (torch.rand(C, generator=g) + 0.5) if weighted else None
+    min_kept = N * H * W // 16
+    up = c_oracle.bilinear_nhwc_to_nchw(lo.numpy(), C, H, W)
+    ref = c_oracle.ohem(up, labels.numpy(), 255, 0.7, min_kept, class_weight=None if cwt is None else cwt.numpy())
+    lo_dev = lo.to(cuda).permute(0, 3, 1, 2)[:, :C].requires_grad_(True)
+    loss = ops.OhemUpCEFn.apply(lo_dev, labels.to(cuda), H, W, C, 255, 0.7, min_kept, None if cwt is None else cwt.to(cuda))
+    loss.backward(retain_graph=True)
+    _, _, p, state, _ = loss.grad_fn.saved_tensors
+    st = ops.ohem_state_dict(state)
+    p = p.cpu().numpy()
+    assert np.array_equal(p.view(np.uint32), ref["p"].view(np.uint32))
+    kept = (labels.numpy().reshape(-1) != 255) & ((not st["active"]) | (p <= np.float32(st["T"])))
+    assert np.array_equal(kept, ref["kept"])
+    assert abs(loss.item() - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    lo_t = lo[..., :C].permute(0, 3, 1, 2).clone().requires_grad_(True)
+    l2 = torch_ref.ohem_ce(F.interpolate(lo_t, scale_factor=s, mode="bilinear", align_corners=True), labels, 255, 0.7,
+                           min_kept, weight=cwt)
+    l2.backward()
+    assert rel_err(lo_dev.grad, lo_t.grad) < 1e-3
+
+
+def test_ohem_exact_kernels_match_generic_at_full_size(cuda):
+    """BASELINE size (16 x 19 x 1024 x 1024, x8): the exact-class-count kernels against the generic band kernels
+    (tsb_debug_set key 10) on the same input: identical p bits / threshold / loss, gradients equal to fp32 summation order"""
+    ops = _ops()
+    N, C, h, w, s = 16, 19, 128, 128, 8
+    H, W = h * s, w * s
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lo = torch.randn(N, h, w, 32, device=cuda, generator=g) * 3
+    labels = torch.randint(0, C, (N, H, W), device=cuda, generator=g)
+    labels[:, :100] = 255
+    min_kept = N * H * W // 16
+    res = []
+    try:
+        for flag in (1, 0):
+            ops.call("tsb_debug_set", 10, flag)
+            lo_v = lo.permute(0, 3, 1, 2)[:, :C].detach().requires_grad_(True)
+            loss = ops.OhemUpCEFn.apply(lo_v, labels, H, W, C, 255, 0.7, min_kept, None)
+            loss.backward(retain_graph=True)
+            _, _, p, state, _ = loss.grad_fn.saved_tensors
+            res.append((p.clone(), ops.ohem_state_dict(state), loss.item(), lo_v.grad.clone()))
+    finally:
+        ops.call("tsb_debug_set", 10, 1)
+    (p1, s1, l1, g1), (p0, s0, l0, g0) = res
+    assert torch.equal(p1.view(torch.int32), p0.view(torch.int32))
+    assert s1["T"] == s0["T"] and s1["kept"] == s0["kept"] and s1["active"] == s0["active"]
+    assert abs(l1 - l0) <= 1e-6 * abs(l0)
+    assert rel_err(g1, g0) < 1e-4

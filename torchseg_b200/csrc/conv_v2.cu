@@ -619,6 +619,7 @@ int launch_v2(const V2Params& prm, int grid_x, int n_tiles, size_t smem, cudaStr
 }  // namespace
 
 extern int g_tsb_ohem_hoist;
+extern int g_tsb_ohem_exact;
 extern "C" int tsb_debug_set(int key, int value) {
     if (key == 1) g_use_base_offset = value;
     else if (key == 2) g_allow_rows = value;
@@ -629,6 +630,7 @@ extern "C" int tsb_debug_set(int key, int value) {
     else if (key == 7) g_allow_pair = value;
     else if (key == 8) convv2::g_allow_taps = value;
     else if (key == 9) g_allow_wide_io = value;
+    else if (key == 10) g_tsb_ohem_exact = value;
     else return TSB_ERR_ARG;
     return TSB_OK;
 }

@@ -597,12 +597,226 @@ ohem_grad_up_kernel(const float* __restrict__ lo, int cs, int h, int w, const in
     }
 }
 
+
+// =============================================================================================
+// Exact-class-count band kernels (CX = 19 Cityscapes, 21 VOC): second generation of the fused-upsample pair.
+// ncu (profiles/r02_hot): the generic p_target kernel was ISSUE bound at 1005 warp-instructions per pixel, 40 % of them
+// run-time `c < C` guards, `c == t` selects, the branch inside exp_det and the four-tap blend redone for every row; the
+// gradient kernel ran at 54 % issue utilisation with 128 registers (2 CTAs / SM) and 105 ISETP per pixel.
+//   * CX is a compile-time constant: no class guards, full unrolling;
+//   * the horizontally blended source rows T0/T1[c][x] (row-invariant) are staged ONCE per band in shared memory, each
+//     thread in its own column (no synchronisation): a row costs 2 LDS + 3 flops per class instead of 4 LDS + 9;
+//   * the target class is fetched by ONE dynamic shared-memory read pair (its exp is recomputed: bit-identical, same
+//     inputs) instead of CX compare-selects;
+//   * gradient: the one-hot term goes straight to a low-resolution shared-memory accumulator (4 RED.shared per pixel) instead
+//     of CX compare-selects; the accumulators' hand-over to phase 2 re-uses the T arrays in place (thread-private
+//     columns), which leaves ~80 registers and 3 CTAs / SM.
+// Arithmetic (operation order, roundings) is unchanged: p, T and the kept set stay bit-exact against the oracle.
+// =============================================================================================
+constexpr int kPitchX = kStrip + 1;
+
+template <int CX>
+__global__ void __launch_bounds__(kThreads, 3)
+ohem_ptarget_up_x_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64_t* __restrict__ labels, int N,
+                         int H, int W, int ignore_label, float thresh, float* __restrict__ p, float* __restrict__ nll,
+                         uint32_t* state, int maxcols) {
+    __shared__ float s_red[33];
+    extern __shared__ float s_dyn_x[];           // sT0[CX][kPitchX] | sT1[CX][kPitchX] | s_lo0[maxcols][CX] | s_lo1[...]
+    float* sT0 = s_dyn_x;
+    float* sT1 = s_dyn_x + CX * kPitchX;
+    float* s_lo0 = s_dyn_x + 2 * CX * kPitchX;
+    float* s_lo1 = s_lo0 + maxcols * CX;
+    PtAccum acc;
+    const float ry = area_scale(h, H), rx = area_scale(w, W);
+    const int n = blockIdx.z, ci = blockIdx.y, x0 = blockIdx.x * kStrip, x1 = min(W, x0 + kStrip);
+    const int i1 = ci + (ci < h - 1 ? 1 : 0);
+    const BandGeom g = band_geom(ry, rx, ci, x0, x1, H, w);
+    if (g.ncols > maxcols) __trap();
+    for (int q = threadIdx.x; q < 2 * g.ncols * CX; q += kThreads) {
+        const int c = q % CX, t2 = q / CX, col = t2 % g.ncols, row = t2 / g.ncols;
+        (row ? s_lo1 : s_lo0)[col * CX + c] = __ldg(lo + (((long long)n * h + (row ? i1 : ci)) * w + g.jbase + col) * cs + c);
+    }
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const int x = x0 + tid;
+    const bool xin = x < x1;
+    const Lerp lx = make_lerp(rx, xin ? x : x0, w);
+    const int j0 = lx.i0 - g.jbase, j1 = lx.i1 - g.jbase;
+#pragma unroll
+    for (int c = 0; c < CX; ++c) {
+        sT0[c * kPitchX + tid] = lerp_h(lx, s_lo0[j0 * CX + c], s_lo0[j1 * CX + c]);
+        sT1[c * kPitchX + tid] = lerp_h(lx, s_lo1[j0 * CX + c], s_lo1[j1 * CX + c]);
+    }
+    long long lab_next = xin ? labels[((long long)n * H + g.y_lo) * W + x] : 0;
+    for (int y = g.y_lo; y <= g.y_hi; ++y) {
+        const long long lab = lab_next;
+        if (xin && y < g.y_hi) lab_next = labels[((long long)n * H + y + 1) * W + x];
+        const Lerp ly = make_lerp(ry, y, h);
+        if (ly.i0 != ci || !xin) continue;  // uniform in y across the CTA
+        const long long i = ((long long)n * H + y) * W + x;
+        const bool valid = lab != (long long)ignore_label;
+        const int t = valid ? (int)lab : 0;
+        float v[CX];
+#pragma unroll
+        for (int c = 0; c < CX; ++c) v[c] = lerp_v(ly, sT0[c * kPitchX + tid], sT1[c * kPitchX + tid]);
+        float m = v[0];
+#pragma unroll
+        for (int c = 1; c < CX; ++c) m = fmaxf(m, v[c]);
+        float ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CX; ++c) ssum = __fadd_rn(ssum, tsb_exp_det(__fsub_rn(v[c], m)));
+        // target class: same operands, same operations as v[t] above → identical bits
+        const float xt = lerp_v(ly, sT0[t * kPitchX + tid], sT1[t * kPitchX + tid]);
+        const float et = tsb_exp_det(__fsub_rn(xt, m));
+        const float p_t = __fdiv_rn(et, ssum);
+        const float nl = logf(ssum) - (xt - m);
+        pt_emit(i, valid, p_t, nl, thresh, p, nll, acc);
+    }
+    pt_flush(acc, state, s_red);
+}
+
+template <int CX>
+__global__ void __launch_bounds__(kThreads, 3)
+ohem_grad_up_x_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64_t* __restrict__ labels,
+                      const float* __restrict__ p, int N, int H, int W, int ignore_label, const float* __restrict__ cw,
+                      const uint32_t* __restrict__ state, const float* __restrict__ gscale, float* __restrict__ dlo,
+                      int maxcols) {
+    extern __shared__ float s_dyn_x[];   // sT0 / s_g0 [CX][kPitchX] | sT1 / s_g1 | s_lo0 | s_lo1 | s_oh[2][maxcols][CX]
+    float* sT0 = s_dyn_x;
+    float* sT1 = s_dyn_x + CX * kPitchX;
+    float* s_lo0 = s_dyn_x + 2 * CX * kPitchX;
+    float* s_lo1 = s_lo0 + maxcols * CX;
+    float* s_oh = s_lo1 + maxcols * CX;  // one-hot part of the gradient, already at low resolution: [row][col][c]
+    __shared__ float s_l0[kStrip], s_l1[kStrip];
+    __shared__ short s_seg[kStrip + 8];
+    const bool active = state[ST_ACTIVE] != 0;
+    const float Tth = __uint_as_float(state[ST_THRESH]);
+    const float scale = __uint_as_float(state[ST_INVDEN]) * (gscale ? *gscale : 1.f);
+    const float ry = area_scale(h, H), rx = area_scale(w, W);
+    const int n = blockIdx.z, ci = blockIdx.y, x0 = blockIdx.x * kStrip, x1 = min(W, x0 + kStrip);
+    const int nx = x1 - x0;
+    const int i1 = ci + (ci < h - 1 ? 1 : 0);
+    const BandGeom g = band_geom(ry, rx, ci, x0, x1, H, w);
+    if (g.ncols > maxcols) __trap();
+    for (int q = threadIdx.x; q < 2 * g.ncols * CX; q += kThreads) {
+        const int c = q % CX, t2 = q / CX, col = t2 % g.ncols, row = t2 / g.ncols;
+        (row ? s_lo1 : s_lo0)[col * CX + c] = __ldg(lo + (((long long)n * h + (row ? i1 : ci)) * w + g.jbase + col) * cs + c);
+        s_oh[q] = 0.f;
+    }
+    const int tid = threadIdx.x;
+    const int x = x0 + tid;
+    const bool xin = x < x1;
+    const Lerp lx = make_lerp(rx, xin ? x : x0, w);
+    const int j0 = lx.i0 - g.jbase, j1 = lx.i1 - g.jbase;
+    s_l0[tid] = xin ? lx.l0 : 0.f;
+    s_l1[tid] = xin ? lx.l1 : 0.f;
+    for (int q = tid; q < g.ncols + 2; q += kThreads) s_seg[q] = (short)nx;
+    __syncthreads();
+    if (xin) {
+        const int jprev = (tid == 0) ? -1 : (make_lerp(rx, x - 1, w).i0 - g.jbase);
+        for (int jj = jprev + 1; jj <= j0; ++jj) s_seg[jj] = (short)tid;
+    }
+#pragma unroll
+    for (int c = 0; c < CX; ++c) {
+        sT0[c * kPitchX + tid] = lerp_h(lx, s_lo0[j0 * CX + c], s_lo0[j1 * CX + c]);
+        sT1[c * kPitchX + tid] = lerp_h(lx, s_lo1[j0 * CX + c], s_lo1[j1 * CX + c]);
+    }
+    // ---- phase 1: per-thread accumulation over the rows of the band
+    float G0[CX], G1[CX];
+#pragma unroll
+    for (int c = 0; c < CX; ++c) { G0[c] = 0.f; G1[c] = 0.f; }
+    float* oh00 = s_oh + j0 * CX;                       // (row i, col j0), (i, j1), (i1, j0), (i1, j1)
+    float* oh01 = s_oh + j1 * CX;
+    float* oh10 = s_oh + (g.ncols + j0) * CX;
+    float* oh11 = s_oh + (g.ncols + j1) * CX;
+    long long lab_next = 0;
+    float p_next = 0.f;
+    if (xin) {
+        const long long q0 = ((long long)n * H + g.y_lo) * W + x;
+        lab_next = labels[q0];
+        p_next = active ? p[q0] : 0.f;
+    }
+    for (int y = g.y_lo; y <= g.y_hi; ++y) {
+        const long long lab = lab_next;
+        const float pv = p_next;
+        if (xin && y < g.y_hi) {
+            const long long q1 = ((long long)n * H + y + 1) * W + x;
+            lab_next = labels[q1];
+            p_next = active ? p[q1] : 0.f;
+        }
+        const Lerp ly = make_lerp(ry, y, h);
+        if (ly.i0 != ci || !xin) continue;
+        const bool kept = (lab != (long long)ignore_label) && (!active || pv <= Tth);
+        if (!kept) continue;
+        const int t = (int)lab;
+        const float wt = (cw ? __ldg(cw + t) : 1.f) * scale;
+        float v[CX];
+#pragma unroll
+        for (int c = 0; c < CX; ++c) v[c] = lerp_v(ly, sT0[c * kPitchX + tid], sT1[c * kPitchX + tid]);
+        float m = v[0];
+#pragma unroll
+        for (int c = 1; c < CX; ++c) m = fmaxf(m, v[c]);
+        float ssum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CX; ++c) { v[c] = __expf(v[c] - m); ssum += v[c]; }
+        const float inv = wt / ssum;
+#pragma unroll
+        for (int c = 0; c < CX; ++c) {
+            const float gg = v[c] * inv;               // softmax part; the one-hot part goes to s_oh below
+            G0[c] = fmaf(ly.l0, gg, G0[c]);
+            G1[c] = fmaf(ly.l1, gg, G1[c]);
+        }
+        const float a0 = -wt * ly.l0, a1 = -wt * ly.l1;
+        atomicAdd(oh00 + t, a0 * lx.l0);
+        atomicAdd(oh01 + t, a0 * lx.l1);
+        atomicAdd(oh10 + t, a1 * lx.l0);
+        atomicAdd(oh11 + t, a1 * lx.l1);
+    }
+    // hand-over to phase 2 in place: column `tid` of sT0 / sT1 was only ever read by this thread
+#pragma unroll
+    for (int c = 0; c < CX; ++c) { sT0[c * kPitchX + tid] = G0[c]; sT1[c * kPitchX + tid] = G1[c]; }
+    __syncthreads();
+    // ---- phase 2 (once per band): low-res column j receives the l0x-weighted sum of its own segment and the
+    //      l1x-weighted sum of the previous segment (or of its own when the stencil is clamped at the last column)
+    const int npairs = g.ncols * CX;
+    for (int q = tid; q < npairs; q += kThreads) {
+        const int j = q / CX, c = q - j * CX;
+        const float* g0 = sT0 + c * kPitchX;
+        const float* g1 = sT1 + c * kPitchX;
+        const int a0 = s_seg[j], a1 = s_seg[j + 1];
+        float top = s_oh[j * CX + c], bot = s_oh[(g.ncols + j) * CX + c];
+        for (int xx = a0; xx < a1; ++xx) {
+            const float wl = s_l0[xx];
+            top = fmaf(wl, g0[xx], top);
+            bot = fmaf(wl, g1[xx], bot);
+        }
+        const bool clamped = (g.jbase + j == w - 1);
+        const int b0 = clamped ? a0 : (j > 0 ? (int)s_seg[j - 1] : 0);
+        const int b1 = clamped ? a1 : (j > 0 ? a0 : 0);
+        for (int xx = b0; xx < b1; ++xx) {
+            const float wr = s_l1[xx];
+            top = fmaf(wr, g0[xx], top);
+            bot = fmaf(wr, g1[xx], bot);
+        }
+        if (clamped && j > 0) {
+            for (int xx = s_seg[j - 1]; xx < a0; ++xx) {
+                const float wr = s_l1[xx];
+                top = fmaf(wr, g0[xx], top);
+                bot = fmaf(wr, g1[xx], bot);
+            }
+        }
+        if (top != 0.f) atomicAdd(dlo + (((long long)n * h + ci) * w + g.jbase + j) * cs + c, top);
+        if (bot != 0.f) atomicAdd(dlo + (((long long)n * h + i1) * w + g.jbase + j) * cs + c, bot);
+    }
+}
+
 }  // namespace
 
 // A/B switch (tsb_debug_set key 6): band kernels keep the horizontally blended source rows in registers; bit 0 =
 // gradient kernel (measured 2.16 -> 1.85 ms/step), bit 1 = p_target kernel (measured slower: 111 registers halve the
 // occupancy of an issue-bound kernel, 1.72 -> 1.85 ms) — default 1.
 int g_tsb_ohem_hoist = 1;
+int g_tsb_ohem_exact = 1;   // tsb_debug_set key 10: exact-class-count band kernels (C = 19 / 21)
 
 // =============================================================================================
 // C ABI
@@ -650,10 +864,25 @@ extern "C" int tsb_ohem_ptarget_up(const float* logits_lo, int cs, int h, int w,
                 "tsb_ohem_ptarget_up: bad shape (C must be <= 32)");
     TSB_REQUIRE(N <= 65535 && h <= 65535, "tsb_ohem_ptarget_up: N and h must fit a grid dimension");
     const int maxcols = band_maxcols(w, W);
+    dim3 grid((W + kStrip - 1) / kStrip, h, N);
+    if (g_tsb_ohem_exact && (C == 19 || C == 21)) {      // exact-class-count kernels (Cityscapes / VOC)
+        const size_t smx = sizeof(float) * (2 * (size_t)C * kPitchX + 2 * (size_t)maxcols * C);
+        if (smx <= 100 * 1024) {
+#define LX(CX)                                                                                                      \
+    do {                                                                                                            \
+        int rc_ = tsb_ensure_dyn_smem(reinterpret_cast<const void*>(ohem_ptarget_up_x_kernel<CX>), smx);            \
+        if (rc_) return rc_;                                                                                        \
+        ohem_ptarget_up_x_kernel<CX><<<grid, kThreads, smx, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, H, W, ignore_label, thresh, p, nll, state, maxcols); \
+    } while (0)
+            if (C == 19) LX(19); else LX(21);
+#undef LX
+            TSB_CUDA_CHECK_LAUNCH("ohem_ptarget_up_x");
+            return TSB_OK;
+        }
+    }
     const int cmax = C <= 20 ? 20 : 32;
     const size_t smem = sizeof(float) * 2 * (size_t)maxcols * cmax;
     TSB_REQUIRE(smem <= 28 * 1024, "tsb_ohem_ptarget_up: up-scale factor W/w too small for the band kernel");
-    dim3 grid((W + kStrip - 1) / kStrip, h, N);
 #define L(CM, HO) ohem_ptarget_up_kernel<CM, HO><<<grid, kThreads, smem, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, N, C, H, W, ignore_label, thresh, p, nll, state, maxcols)
     if (C <= 20) { if (g_tsb_ohem_hoist & 2) L(20, true); else L(20, false); }
     else { if (g_tsb_ohem_hoist & 2) L(32, true); else L(32, false); }
@@ -719,8 +948,24 @@ extern "C" int tsb_ohem_grad_up(const float* logits_lo, int cs, int h, int w, co
     TSB_REQUIRE(C > 0 && C <= 32 && cs >= C, "tsb_ohem_grad_up: C must be <= 32");
     TSB_REQUIRE(N <= 65535 && h <= 65535, "tsb_ohem_grad_up: N and h must fit a grid dimension");
     const int maxcols = band_maxcols(w, W);
-    const int cmax = C <= 20 ? 20 : 32;
     TSB_REQUIRE(maxcols <= kStrip, "tsb_ohem_grad_up: up-scale factor W/w too small for the band kernel");
+    if (g_tsb_ohem_exact && (C == 19 || C == 21)) {
+        const size_t smx = sizeof(float) * (2 * (size_t)C * kPitchX + 4 * (size_t)maxcols * C);
+        if (smx <= 72 * 1024) {
+            dim3 gridx((W + kStrip - 1) / kStrip, h, N);
+#define GX(CX)                                                                                                      \
+    do {                                                                                                            \
+        int rc_ = tsb_ensure_dyn_smem(reinterpret_cast<const void*>(ohem_grad_up_x_kernel<CX>), smx);               \
+        if (rc_) return rc_;                                                                                        \
+        ohem_grad_up_x_kernel<CX><<<gridx, kThreads, smx, (cudaStream_t)stream>>>(logits_lo, cs, h, w, labels, p, N, H, W, ignore_label, class_weight, state, gscale, dlogits_lo, maxcols); \
+    } while (0)
+            if (C == 19) GX(19); else GX(21);
+#undef GX
+            TSB_CUDA_CHECK_LAUNCH("ohem_grad_up_x");
+            return TSB_OK;
+        }
+    }
+    const int cmax = C <= 20 ? 20 : 32;
     const size_t smem = sizeof(float) * (2 * (size_t)cmax * (kStrip + 1) + 2 * (size_t)maxcols * cmax);
     TSB_REQUIRE(smem <= 96 * 1024, "tsb_ohem_grad_up: shared memory budget exceeded");
     dim3 grid((W + kStrip - 1) / kStrip, h, N);

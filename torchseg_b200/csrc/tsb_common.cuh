@@ -166,7 +166,10 @@ template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bf
 // Valid for x <= 0 (softmax arguments after max subtraction); returns 0 below -86.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tsb_exp_det(float x) {
-    if (x < -86.0f) return 0.0f;   // < 4.5e-38: cannot change a sum containing exp(0) = 1; keeps all results normal
+    // branch-free: inputs below -86 (< 4.5e-38: cannot change a sum containing exp(0) = 1; keeps all results normal) are
+    // evaluated at -86 and replaced by 0 with one select — a branch per class cost ~6 issue slots in the OHEM kernels
+    const bool tiny = x < -86.0f;
+    x = tiny ? -86.0f : x;
     const float LOG2E = 1.4426950408889634f;
     const float LN2_HI = 0.693145751953125f;          // 0x3f317200
     const float LN2_LO = 1.428606765330187e-06f;      // ln2 - LN2_HI
@@ -188,7 +191,8 @@ __device__ __forceinline__ float tsb_exp_det(float x) {
     p = fmaf(p, r, 1.0f);
     // p * 2^n on the exponent field (exact: the result is normal). (bits(z) << 23) == (n << 23) mod 2^32 because the
     // magic constant's own bits are shifted out.
-    return __int_as_float(__float_as_int(p) + (int)((unsigned)__float_as_int(z) << 23));
+    const float e = __int_as_float(__float_as_int(p) + (int)((unsigned)__float_as_int(z) << 23));
+    return tiny ? 0.0f : e;
 }
 
 #endif  // __CUDACC__
