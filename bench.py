@@ -424,15 +424,17 @@ def main():
     if args.model == "pspnet":
         MODEL, NUM_CLASSES, IGNORE = "pspnet", 150, -1
         H = W = args.size or 480
-        STEP_GFLOP_PER_IMG = 1588.7 * (H * W) / (480.0 * 480.0)   # BASELINE.md §2 (529.62 GF fwd @480^2)
+        # 529.62 GF fwd @480^2 (step 1588.7); 1190.8 GF fwd @713^2 (90x90 feature map) ⇒ step 3 x 1190.8 - 0.45
+        STEP_GFLOP_PER_IMG = (3 * 1190.8 - 0.45) if H == 713 else 1588.7 * (H * W) / (480.0 * 480.0)
         METRIC = "images/sec training step (%dx%d, 150-class)" % (H, W)
         WORKLOAD = "PSPNet-R101_v1c dilated-8 train step, %dx%d, 150-class CE (BASELINE configs[2] family, reference shape 480)" % (H, W)
     elif args.model == "psanet":
         MODEL, NUM_CLASSES, IGNORE = "psanet", 150, -1
-        H = W = 480    # the PSA head needs exactly 60x60 = 3600 positions (psanet network.py:88)
-        STEP_GFLOP_PER_IMG = 3 * (590.03 + 26.5) - 2 * 0.10    # conv 590.03 GF + bmm 26.5 GF fwd @480^2
-        METRIC = "images/sec training step (480x480, 150-class)"
-        WORKLOAD = "PSANet-R101_v1c dilated-8 train step, 480x480, 150-class CE (SURVEY C5); conv + PSA bmm FLOPs"
+        H = W = args.size or 480    # the PSA head needs exactly 60x60 = 3600 positions (psanet network.py:88): 473..480
+        # conv 590.03 GF (@480; 589.58 @473) + bmm 26.5 GF fwd
+        STEP_GFLOP_PER_IMG = 3 * ((589.58 if H == 473 else 590.03) + 26.5) - 2 * 0.10
+        METRIC = "images/sec training step (%dx%d, 150-class)" % (H, W)
+        WORKLOAD = "PSANet-R101_v1c dilated-8 train step, %dx%d, 150-class CE (SURVEY C5 / BASELINE configs[4] at 473); conv + PSA bmm FLOPs" % (H, W)
     elif args.model == "dfn":
         MODEL = "dfn"
         H = W = args.size or 1024
@@ -487,6 +489,11 @@ def main():
     # The whole step (zero_grad → forward → backward → [bucketed NCCL gradient all-reduce on the side stream, NVLink SyncBN
     # exchanges] → fused SGD) is ONE CUDA graph replay (torchseg_b200.engine.graph.GraphedTrainStep) unless --no-graph /
     # capture is unavailable; the eager-launch time of the same step is measured and reported beside it.
+    # eager launches first (DDP in its overlapped mode), then the graph: no autograd graph of an eager step may be alive
+    # when the capture starts, so only the loss VALUE is kept
+    ms_eager, clk_eager, launches_eager, loss = timed_eager(args.steps)
+    ms, clk, launches, final_loss = ms_eager, clk_eager, launches_eager, float(loss.item())
+    del loss
     gstep = None
     if args.graph and (world == 1 or os.environ.get("TSB_BENCH_GRAPH_MULTI", "1") != "0"):
         from torchseg_b200.engine.graph import GraphedTrainStep
@@ -498,8 +505,6 @@ def main():
         if float(ok.item()) < 1.0:
             sys.stderr.write("bench: CUDA graph capture unavailable (%s); eager step timed instead\n" % gstep.error)
             gstep = None
-    ms_eager, clk_eager, launches_eager, loss = timed_eager(args.steps)
-    ms, clk, launches, final_loss = ms_eager, clk_eager, launches_eager, float(loss.item())
     if gstep is not None:
         static_in = gstep.static_inputs
         for _ in range(2):
