@@ -522,3 +522,36 @@ def test_bisenet_eval_bn_folding_matches_unfolded(cuda):
         model.ffm.conv_1x1.bn.weight.mul_(1.5)
         changed = model(x)
     assert norm_err(changed, outs[True]) > 1e-3
+
+
+def test_pspnet_odd_input_size_matches_oracle(cuda):
+    """BASELINE configs[2] asks for 713 x 713 (not a multiple of 8): the heads up-sample to the INPUT size (`size=`
+    semantics, identical numbers to scale_factor=8 where that is defined), the stem pads the odd image. Small odd size
+    here (105 → 53 → 27 → 14 feature map), loss against the oracle patched the same way (oracle/torch_ref._up8)."""
+    import torchseg_b200
+    from torchseg_b200.networks import PSPNet
+    from oracle import torch_ref
+    torch.manual_seed(4)
+    N, HW = 4, 105
+    m = PSPNet(150, torch.nn.CrossEntropyLoss(ignore_index=-1))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout2d):
+            mod.p = 0.0
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, 3, HW, HW, generator=g)
+    y = torch.randint(-1, 150, (N, HW, HW), generator=g)
+    loss_ref, (psp_ref, _) = torch_ref.pspnet_loss(x, y, sd)
+    assert tuple(psp_ref.shape[2:]) == (HW, HW)
+    m.to(cuda)
+    torchseg_b200.prepare_model(m)
+    m.train()
+    loss = m(x.to(cuda), y.to(cuda))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 1e-2 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    m.eval()
+    with torch.no_grad():
+        out = m(x.to(cuda))
+    assert tuple(out.shape) == (N, 150, HW, HW)

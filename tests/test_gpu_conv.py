@@ -232,3 +232,26 @@ def test_wgrad_taps_matches_row_kernel(cuda):
     finally:
         ops.call("tsb_debug_set", 8, 1)
     assert rel_err(outs[0], outs[1]) < 1e-4
+
+
+@pytest.mark.parametrize("HW,R", [((57, 75), 3), ((45, 34), 7)])
+def test_stem_odd_image_size(cuda, HW, R):
+    """odd input sizes (BASELINE configs[2] 713, configs[4] 473): the space-to-depth pack pads one zero row / column, which
+    is the stem's own zero padding — output identical to F.conv2d on the odd image"""
+    from torchseg_b200 import ops
+    H, W = HW
+    g = torch.Generator().manual_seed(13)
+    N, K = 2, 64
+    img = torch.randn(N, 3, H, W, generator=g)
+    w = bf16_round(torch.randn(K, 3, R, R, generator=g) / 12)
+    y_ref = F.conv2d(bf16_round(img), w, None, 2, (R - 1) // 2)
+    xs = ops.pack_image_s2d(img.to(cuda))
+    He, We = H + (H & 1), W + (W & 1)
+    assert tuple(xs.shape) == (N, 16, He // 2, We // 2 + 4) and tuple(y_ref.shape[2:]) == (He // 2, We // 2)
+    wk = w.to(cuda).permute(0, 2, 3, 1).contiguous()
+    wp = torch.empty((K, 4, 4, 16), dtype=torch.bfloat16, device=cuda)
+    ops.call("tsb_pack_stem_weight", ops.ptr(wk), K, R, ops.ptr(wp), ops.stream())
+    y = ops.nhwc_empty(N, K, He // 2, We // 2)
+    ops.call("tsb_conv_stem_fprop", ops.ptr(xs), N, He, We, ops.ptr(wp), K, ops.ptr(y), K, None, None, ops.stream())
+    torch.cuda.synchronize()
+    assert rel_err(y, y_ref) < 1e-2

@@ -950,6 +950,11 @@ def pack_image_s2d(img):
     """NCHW fp32 image → [N,16,H/2,W/2+4] bf16 (NHWC) operand of the 7x7/2 stems"""
     N, C, H, W = img.shape
     assert C == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    if (H | W) & 1:
+        # odd sizes (713, 473): one extra zero row / column at the bottom / right is exactly the stem's own zero padding
+        # (the stride-2 output size floor((H + 2p - k) / 2) + 1 is the same for H and H + 1 when H is odd)
+        img = torch.nn.functional.pad(img, (0, W & 1, 0, H & 1)).contiguous()
+        H, W = H + (H & 1), W + (W & 1)
     out = nhwc_empty(N, 16, H // 2, W // 2 + 4, device=img.device)
     call("tsb_pack_image_s2d", ptr(img), N, H, W, ptr(out), stream())
     return out
