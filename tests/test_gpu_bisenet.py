@@ -216,18 +216,36 @@ def test_bisenet_step_matches_oracle(cuda):
     stats = {}
     loss_ref, _ = torch_ref.bisenet_r18_loss(x, y, sd, min_kept, stats=stats)   # plain fp32 reference
     loss_ref.backward()
+    grads_ref = {k: v.grad.clone() for k, v in sd.items() if v.grad is not None}
+    for v in sd.values():
+        v.grad = None
+    # the same oracle with bf16 STORAGE emulated: |fp32 − emulation| is what the storage policy alone does to each gradient
+    torch_ref.set_bf16_emulation(True)
+    try:
+        loss_emu, _ = torch_ref.bisenet_r18_loss(x, y, sd, min_kept)
+        loss_emu.backward()
+    finally:
+        torch_ref.set_bf16_emulation(False)
+    grads_emu = {k: v.grad.clone() for k, v in sd.items() if v.grad is not None}
     loss = model(x.to(cuda), y.to(cuda))
     loss.backward()
     torch.cuda.synchronize()
     assert abs(loss.item() - loss_ref.item()) < 1e-2 * abs(loss_ref.item()), (loss.item(), loss_ref.item())
-    bad = []
+    bad, outside = [], []
     for n, p in model.named_parameters():
-        a, b = p.grad.float().cpu().reshape(-1), sd[n].grad.reshape(-1)
-        cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
-        ratio = float(a.norm() / b.norm().clamp_min(1e-30))
+        a, b, c = p.grad.float().cpu(), grads_ref[n], grads_emu[n]
+        af, bf = a.reshape(-1), b.reshape(-1)
+        cos = float(torch.dot(af, bf) / (af.norm() * bf.norm()).clamp_min(1e-30))
+        ratio = float(af.norm() / bf.norm().clamp_min(1e-30))
         if cos < 0.8 or not (0.7 < ratio < 1.4):
             bad.append((n, round(cos, 3), round(ratio, 3)))
+        # every conv / classifier weight: as close to the fp32 oracle as the bf16-storage emulation is (x1.5 + 2e-2)
+        if p.dim() == 4:
+            e, spread = norm_err(a, b), norm_err(c, b)
+            if e > 1.5 * spread + 2e-2:
+                outside.append((n, round(e, 4), round(spread, 4)))
     assert not bad, "gradient direction / magnitude off: %s" % bad[:10]
+    assert not outside, "gradient farther from the fp32 oracle than 1.5 x the bf16-storage spread + 2e-2: %s" % outside[:10]
     msd = model.state_dict()
     for k, v in stats.items():   # running stats: momentum 0.1, unbiased variance
         assert rel_err(msd[k], v) < 3e-2, k
@@ -368,11 +386,12 @@ def test_graphed_train_step_matches_eager(cuda):
     trajectory: same losses step by step (up to the non-deterministic summation order of the atomics), LR changes
     between replays are honoured (push_hyperparams → the device tensor the captured kernel reads)"""
     import os
-    if os.environ.get("TSB_TEST_GRAPH", "0") != "1":
-        # engine/graph.py is EXPERIMENTAL: on this stack the capture is intermittently invalidated, and a failed capture
-        # leaves the process-wide CUDA RNG in capture mode (later torch.randn on the device raise) — so the test only
-        # runs on request and never inside the default `pytest -m gpu` run
-        pytest.skip("set TSB_TEST_GRAPH=1 to exercise the experimental whole-step CUDA graph")
+    if os.environ.get("TSB_TEST_GRAPH", "1") == "0":
+        pytest.skip("TSB_TEST_GRAPH=0")
+    # (round 1 gated this test behind an environment variable: the capture failed "intermittently". Root cause, round 2:
+    # a live autograd graph of an eager step — see engine/graph.py. Nothing of the kind is alive here: the eager trajectory
+    # below keeps only loss.item().)
+    torch.cuda.set_stream(torch.cuda.Stream())
     from torchseg_b200 import optim
     from torchseg_b200.engine.graph import GraphedTrainStep
     from torchseg_b200.utils.init_func import group_weight
@@ -437,6 +456,21 @@ def test_graphed_train_step_matches_eager(cuda):
     assert abs(l_after.item() - graphed[-1]) < 1e-3 * abs(graphed[-1]), (l_after.item(), graphed[-1])
     for p in model.parameters():
         assert torch.isfinite(p).all()
+    step.release()
+    # restore_after_warmup: constructing the object leaves parameters, momentum and BN statistics untouched, and the
+    # first replay then computes the same loss as an eager step from that state
+    model, opt, data = make()
+    before = (opt.flat_param.clone(), opt.flat_mom.clone(), [b.clone() for b in model.buffers()])
+    for g in opt.param_groups:
+        g["lr"] = 0.0
+    step2 = GraphedTrainStep(model, opt, list(data[0]), warmup=2, restore_after_warmup=True)
+    assert step2.graph is not None, step2.error
+    assert torch.equal(opt.flat_param, before[0]) and torch.equal(opt.flat_mom, before[1])
+    assert all(torch.equal(a, b) for a, b in zip(model.buffers(), before[2]))
+    l_graph = step2(*data[0]).item()
+    assert abs(l_graph - eager[0]) < 1e-3 * abs(eager[0]), (l_graph, eager[0])
+    step2.release()
+    torch.cuda.set_stream(torch.cuda.default_stream())
 
 
 def test_bisenet_eval_forward_matches_oracle(cuda):

@@ -32,10 +32,14 @@ import torch
 
 class GraphedTrainStep(object):
     def __init__(self, model, optimizer, example_inputs, warmup=3, enable=True, side_stream_warmup=True,
-                 capture_error_mode=None, ddp=None):
+                 capture_error_mode=None, ddp=None, restore_after_warmup=False):
         """ddp: the apex.parallel.DistributedDataParallel shim wrapping `model` (multi-GPU): its bucketed NCCL all-reduce
         on the side stream (fork / join inside the capture) and the NVLink SyncBN exchanges (device-resident sequence
-        counter) are captured too. Every rank must construct the object at the same point of its program."""
+        counter) are captured too. Every rank must construct the object at the same point of its program.
+        NOTE: construction runs `warmup` REAL optimiser steps on `example_inputs` (a capture needs every lazy allocation
+        and attribute made first): weights, momentum and BN running statistics move, with the learning rate currently in
+        `param_groups`. restore_after_warmup=True snapshots parameters / momentum / module buffers before and puts them
+        back after the capture, so that constructing the object leaves the training state untouched."""
         self.model = model
         self.ddp = ddp
         if ddp is not None:
@@ -56,6 +60,10 @@ class GraphedTrainStep(object):
         if side_stream_warmup and warmup < 1:
             warmup = 1       # at least one step must have run on a non-default stream before the capture
         from .. import _lib
+        snap = None
+        if restore_after_warmup:
+            snap = (optimizer.flat_param.clone(), optimizer.flat_mom.clone(), optimizer._steps,
+                    [b.clone() for b in model.buffers()])
         try:
             if side_stream_warmup:
                 side = torch.cuda.Stream(device=dev)
@@ -86,6 +94,26 @@ class GraphedTrainStep(object):
                     gc.enable()
             self.launches_per_step = _lib.launch_count() - n0
             self.graph = g
+            if snap is not None:     # the capture itself executed nothing; undo the warm-up steps
+                with torch.no_grad():
+                    optimizer.flat_param.copy_(snap[0])
+                    optimizer.flat_mom.copy_(snap[1])
+                    optimizer._steps = snap[2]
+                    for b, v in zip(model.buffers(), snap[3]):
+                        b.copy_(v)
+                from .. import ops
+                ops.pack_cache.invalidate()
+                # the captured kernels read the bf16 MIRROR of the parameters (written by the SGD kernel at the end of every
+                # step): regenerate it from the restored weights with a no-op update (lr 0, weight decay 0, momentum 1,
+                # zero gradient: parameters and momentum come out unchanged)
+                optimizer.flat_grad.zero_()
+                ng = len(optimizer.param_groups)
+                z = torch.zeros(ng, dtype=torch.float32, device=dev)
+                ops.call("tsb_sgd_flat_pack", ops.ptr(optimizer.flat_param), ops.ptr(optimizer.flat_grad), ops.ptr(optimizer.flat_mom),
+                         optimizer.flat_param.numel(), ops.ptr(optimizer._seg_end), ops.ptr(z), ops.ptr(z), ng, 1.0, 1.0, 0,
+                         ops.ptr(optimizer.pack.wb_flat), ops.stream())
+                optimizer.pack.mark_fresh()
+                torch.cuda.synchronize(dev)
         except Exception as e:  # noqa: BLE001 — fall back to eager steps, keep the reason
             import traceback
             tb = traceback.extract_tb(e.__traceback__)
