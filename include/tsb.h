@@ -328,6 +328,14 @@ int tsb_train_preprocess(const long long* samples_dev, int n, int crop_h, int cr
                          const float* lut, float img_pad, int gt_pad, float* out_img, long long* out_gt,
                          tsb_stream_t stream);
 
+/* DFN border labels ('aux_label', model/dfn/cityscapes.dfn.R101_v1c/dataloader.py:15-29,38-42): cv2.Canny(apertureSize=7,
+ * thresholds 5, 5) of the scaled label map with 255 → 0, cv2.dilate(7x7 rect), 255 → 1, cropped / padded (255) like the label.
+ * Same sample descriptors as tsb_train_preprocess; integer arithmetic throughout (bit-exact vs cv2). The workspace is the
+ * caller's (tsb_edge_labels_workspace_bytes, 256-byte aligned). */
+size_t tsb_edge_labels_workspace_bytes(int n, int crop_h, int crop_w);
+int tsb_edge_labels(const long long* samples_dev, int n, int crop_h, int crop_w, int gt_pad, void* workspace,
+                    size_t workspace_bytes, long long* out_aux, tsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

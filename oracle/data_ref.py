@@ -108,3 +108,102 @@ def train_pre(img_rgb, gt, params, crop_size, mean, std):
     p_img = _crop_pad(x, pos, crop_size, 0)
     p_gt = _crop_pad(gt, pos, crop_size, 255)
     return np.ascontiguousarray(p_img.transpose(2, 0, 1)).astype(np.float32), np.ascontiguousarray(p_gt).astype(np.int64)
+
+
+# --------------------------------------------------------------------------------------------------
+# DFN border labels — /root/reference/model/dfn/cityscapes.dfn.R101_v1c/dataloader.py:15-29:
+#   no255_gt = gt with 255 → 0; cgt = cv2.Canny(no255_gt, 5, 5, apertureSize=7); cgt = cv2.dilate(cgt, 7x7 rect); 255 → 1
+# OpenCV's Canny for apertureSize = 7 (imgproc/src/canny.cpp): thresholds /16 then floor (5 → 0), dx / dy =
+# Sobel(ksize 7, scale 1/16, BORDER_REPLICATE) as int16 (round half to even), magnitude |dx| + |dy| with a zero border,
+# non-maximum suppression by the fixed-point tangent test (TG22 = round(tan 22.5° · 2^15)), then hysteresis (empty here:
+# low == high). Pinned bit-for-bit against cv2 in tests/test_cpu_data.py.
+# --------------------------------------------------------------------------------------------------
+_SM7 = np.array([1, 6, 15, 20, 15, 6, 1], dtype=np.int64)
+_DV7 = np.array([-1, -4, -5, 0, 5, 4, 1], dtype=np.int64)
+
+
+def sobel7_over16(img):
+    H, W = img.shape
+    p = np.pad(img.astype(np.int64), 3, mode="edge")
+
+    def sep(kx, ky):
+        t = np.zeros((H + 6, W), dtype=np.int64)
+        for i in range(7):
+            t += kx[i] * p[:, i:i + W]
+        o = np.zeros((H, W), dtype=np.int64)
+        for i in range(7):
+            o += ky[i] * t[i:i + H, :]
+        return o
+
+    def rnd(v):
+        return np.clip(np.rint(v / 16.0), -32768, 32767).astype(np.int64)
+
+    return rnd(sep(_DV7, _SM7)), rnd(sep(_SM7, _DV7))
+
+
+def canny_ap7(img, low_t=5, high_t=5):
+    """cv2.Canny(img, low_t, high_t, apertureSize=7) (L1 gradient) for uint8 [H,W]"""
+    low = int(np.floor(low_t / 16.0))
+    high = int(np.floor(high_t / 16.0))
+    dx, dy = sobel7_over16(img)
+    H, W = img.shape
+    mp = np.pad(np.abs(dx) + np.abs(dy), 1)
+    m = mp[1:-1, 1:-1]
+    TG22 = int(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
+    x = np.abs(dx)
+    y = np.abs(dy) << 15
+    tg22x = x * TG22
+    tg67x = tg22x + (x << 16)
+    s = np.where((dx ^ dy) < 0, -1, 1)
+    jj = np.arange(W)[None, :] + 1
+    ii = np.arange(H)[:, None] + 1
+    horiz = (y < tg22x) & (m > mp[1:-1, 0:-2]) & (m >= mp[1:-1, 2:])
+    vert = (y >= tg22x) & (y > tg67x) & (m > mp[0:-2, 1:-1]) & (m >= mp[2:, 1:-1])
+    diag = (y >= tg22x) & (y <= tg67x) & (m > mp[ii - 1, jj - s]) & (m > mp[ii + 1, jj + s])
+    cand = (m > low) & (horiz | vert | diag)
+    strong = cand & (m > high)
+    weak = cand & ~strong
+    if weak.any():                       # hysteresis: only when low < high (not the DFN call)
+        out = strong.copy()
+        stack = list(zip(*np.nonzero(strong)))
+        while stack:
+            i, j = stack.pop()
+            for di in (-1, 0, 1):
+                for dj in (-1, 0, 1):
+                    a, b = i + di, j + dj
+                    if 0 <= a < H and 0 <= b < W and weak[a, b] and not out[a, b]:
+                        out[a, b] = True
+                        stack.append((a, b))
+        strong = out
+    return (strong * 255).astype(np.uint8)
+
+
+def dilate7(img):
+    """cv2.dilate(img, cv2.getStructuringElement(cv2.MORPH_RECT, (7, 7))) for a non-negative uint8 map"""
+    H, W = img.shape
+    p = np.pad(img, 3)
+    out = np.zeros_like(img)
+    for i in range(7):
+        for j in range(7):
+            out = np.maximum(out, p[i:i + H, j:j + W])
+    return out
+
+
+def train_pre_dfn(img_rgb, gt, params, crop_size, mean, std):
+    """DFN TrainPre.__call__ (dfn dataloader.py:15-44): as train_pre plus the border label 'aux_label' ∈ {0, 1, 255}"""
+    if params["flip"]:
+        img_rgb = img_rgb[:, ::-1]
+        gt = gt[:, ::-1]
+    img_rgb = resize_linear_u8(np.ascontiguousarray(img_rgb), params["sw"], params["sh"])
+    gt = resize_nearest(np.ascontiguousarray(gt), params["sw"], params["sh"])
+    no255 = gt.copy()
+    no255[gt == 255] = 0
+    cgt = dilate7(canny_ap7(no255, 5, 5))
+    cgt[cgt == 255] = 1
+    x = ((img_rgb.astype(np.float32) / 255.0) - mean) / std
+    pos = (params["pos_h"], params["pos_w"])
+    p_img = _crop_pad(x, pos, crop_size, 0)
+    p_gt = _crop_pad(gt, pos, crop_size, 255)
+    p_cgt = _crop_pad(cgt, pos, crop_size, 255)
+    return (np.ascontiguousarray(p_img.transpose(2, 0, 1)).astype(np.float32), np.ascontiguousarray(p_gt).astype(np.int64),
+            np.ascontiguousarray(p_cgt).astype(np.int64))

@@ -88,3 +88,18 @@ def pipeline_case(H=100, W=160, crop=(96, 128), seed=1):
     gt[rng.random((H, W)) < 0.05] = 255
     return (bgr, gt, crop, [0.75, 1, 1.25, 1.5, 1.75, 2.0], np.array([0.485, 0.456, 0.406]),
             np.array([0.229, 0.224, 0.225]))
+
+
+def pipeline_case_dfn(H=100, W=160, crop=(96, 128), seed=2):
+    """label map with regions (so that Canny finds borders) + the DFN scale array (dfn config.py:87)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    gt = np.zeros((H, W), np.uint8)
+    for _ in range(30):
+        y0, x0 = rng.integers(0, H), rng.integers(0, W)
+        h, w = rng.integers(3, H // 2), rng.integers(3, W // 2)
+        gt[y0:y0 + h, x0:x0 + w] = rng.integers(0, 19)
+    gt[rng.random((H, W)) < 0.03] = 255
+    return (bgr, gt, crop, [0.5, 0.75, 1, 1.5, 1.75, 2.0], np.array([0.485, 0.456, 0.406]),
+            np.array([0.229, 0.224, 0.225]))

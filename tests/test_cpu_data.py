@@ -9,7 +9,7 @@ import random
 import numpy as np
 import pytest
 
-from golden_cases import pipeline_case
+from golden_cases import pipeline_case, pipeline_case_dfn
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "data_pipeline.json")))
@@ -73,3 +73,35 @@ def test_host_draw_order_and_lut_match_reference_semantics():
     v = np.arange(256, dtype=np.uint8).reshape(256, 1, 1).repeat(3, axis=2)
     ref = (((v.astype(np.float32) / 255.0) - mean) / std).astype(np.float32)      # [256,1,3]
     assert np.array_equal(lut.view(np.uint32), np.ascontiguousarray(ref[:, 0, :].T).view(np.uint32))
+
+
+def test_canny_dilate_restatements_match_cv2_bit_for_bit():
+    """cv2.Canny(apertureSize=7) / cv2.dilate(7x7) as used by the DFN loader (dfn dataloader.py:22-29)"""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import data_ref
+    rng = np.random.default_rng(3)
+    k = cv2.getStructuringElement(cv2.MORPH_RECT, (7, 7))
+    for (H, W) in ((64, 96), (101, 77), (200, 312)):
+        for _ in range(2):
+            g = np.zeros((H, W), np.uint8)
+            for _ in range(40):
+                y0, x0 = rng.integers(0, H), rng.integers(0, W)
+                g[y0:y0 + rng.integers(3, H // 2), x0:x0 + rng.integers(3, W // 2)] = rng.integers(0, 19)
+            g[rng.random((H, W)) < 0.01] = rng.integers(0, 19)
+            ref = cv2.Canny(g, 5, 5, apertureSize=7)
+            mine = data_ref.canny_ap7(g, 5, 5)
+            assert np.array_equal(ref, mine) and int((ref > 0).sum()) > 100
+            assert np.array_equal(cv2.dilate(ref, k), data_ref.dilate7(mine))
+            dx = cv2.Sobel(g, cv2.CV_16S, 1, 0, ksize=7, scale=1 / 16.0, borderType=cv2.BORDER_REPLICATE)
+            assert np.array_equal(dx.astype(np.int64), data_ref.sobel7_over16(g)[0])
+
+
+def test_train_pre_dfn_oracle_vs_live_reference_golden():
+    from oracle import data_ref
+    bgr, gt, crop, scales, mean, std = pipeline_case_dfn()
+    for seed, ent in GOLD["cases_dfn"].items():
+        random.seed(int(seed))
+        prm = data_ref.draw_params(bgr.shape[:2], crop, scales)
+        data, label, aux = data_ref.train_pre_dfn(bgr[:, :, ::-1], gt, prm, crop, mean, std)
+        assert _sha(data) == ent["data_sha256"] and _sha(label) == ent["label_sha256"], seed
+        assert _sha(aux) == ent["aux_sha256"] and int((aux == 1).sum()) == ent["aux_ones"], seed

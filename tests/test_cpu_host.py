@@ -367,3 +367,60 @@ def test_pack_cache_is_bounded_and_packed_image_matches_by_identity(monkeypatch)
     assert len(packs) == 4
     seg_oprs._release_packed_image()
     assert not seg_oprs._s2d_cache
+
+
+# ------------------------------------------------------------------------------------------------- evaluator worker pool
+class _ToyDataset(object):
+    def __init__(self, n):
+        self.n = n
+
+    def get_length(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        g = torch.Generator().manual_seed(idx)
+        return dict(data=torch.rand(6, 8, 3, generator=g).numpy().astype("float32") * 255,
+                    label=torch.randint(0, 3, (6, 8), generator=g).numpy(), fn=str(idx), n=self.n)
+
+
+class _ToyNet(nn.Module):
+    def __init__(self):
+        super(_ToyNet, self).__init__()
+        self.conv = nn.Conv2d(3, 3, 1)
+
+    def forward(self, x):
+        return torch.log_softmax(self.conv(x), dim=1)
+
+
+def _toy_evaluator(devices):
+    from torchseg_b200.engine.evaluator import Evaluator
+
+    class _Ev(Evaluator):
+        def func_per_iteration(self, data, device):
+            pred = self.whole_eval(data['data'], None, device=None)
+            return dict(idx=int(data['fn']), correct=int((pred == data['label']).sum()), labeled=int(data['label'].size))
+
+        def compute_metric(self, results):
+            c = sum(r['correct'] for r in results)
+            return "n=%d correct=%d order=%s" % (len(results), c, sorted(r['idx'] for r in results))
+
+    import numpy as np
+    torch.manual_seed(0)
+    ev = _Ev(_ToyDataset(7), 3, np.array([0.5, 0.5, 0.5]), np.array([0.25, 0.25, 0.25]), None, [1.0], False, devices)
+    ev.val_func = _ToyNet()
+    return ev
+
+
+def test_evaluator_worker_pool_matches_single_process():
+    """furnace/engine/evaluator.py:97-163: the per-device worker pool (spawned processes, contiguous dataset shreds, results
+    queue) returns the same metric line as the single-process loop — host logic, run here with two CPU 'devices'"""
+    single = _toy_evaluator(["cpu"]).single_process_evalutation()
+    one = _toy_evaluator(["cpu"]).multi_process_evaluation()           # nr_devices == 1 branch (:134-143)
+    assert one == single
+    import multiprocessing
+    if multiprocessing.get_start_method(allow_none=True) not in (None, "fork", "spawn", "forkserver"):
+        pytest.skip("no usable multiprocessing start method")
+    ev = _toy_evaluator(["cpu", "cpu"])
+    ev.context = multiprocessing.get_context("fork")     # (classes defined inside a test module do not survive 'spawn' pickling)
+    pooled = ev.multi_process_evaluation()
+    assert pooled == single and "n=7" in pooled

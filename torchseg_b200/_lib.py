@@ -75,9 +75,10 @@ _SIGS = {
     "tsb_pack_wt_multi": [P, P, P, P, I, I, P],
     "tsb_sigmoid_focal_fwd_bwd": [P, I, P, L, I, F, F, P, P, P],
     "tsb_train_preprocess": [P, I, I, I, I, P, F, I, P, P, P],
+    "tsb_edge_labels": [P, I, I, I, I, P, c_size_t, P, P],
     "tsb_p2p_allreduce_sum": [P, I, P, I, I, c_uint, P, I, I, P, P, P],
 }
-EXPORTS = sorted(list(_SIGS) + ["tsb_last_error", "tsb_version", "tsb_launch_count", "tsb_p2p_buffer_bytes"])
+EXPORTS = sorted(list(_SIGS) + ["tsb_last_error", "tsb_version", "tsb_launch_count", "tsb_p2p_buffer_bytes", "tsb_edge_labels_workspace_bytes"])
 
 _lib = None
 
@@ -101,6 +102,8 @@ def lib():
         h.tsb_launch_count.restype = c_longlong
         h.tsb_p2p_buffer_bytes.restype = c_size_t
         h.tsb_p2p_buffer_bytes.argtypes = [I, I, I]
+        h.tsb_edge_labels_workspace_bytes.restype = c_size_t
+        h.tsb_edge_labels_workspace_bytes.argtypes = [I, I, I]
         # developer A/B switches (include/tsb.h tsb_debug_set): TSB_DEBUG_SET="6=0,5=2"
         for kv in filter(None, os.environ.get("TSB_DEBUG_SET", "").split(",")):
             k, v = kv.split("=")

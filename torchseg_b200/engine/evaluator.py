@@ -9,8 +9,9 @@ reference, so that predictions can be compared pixel by pixel: cv2 resizing of t
 accumulated score map back to the original size. Quirks kept: overlapping windows are SUMMED, not averaged
 (`score = data_scale`, evaluator.py:241-242); flipped scores are added before `exp` is taken.
 
-Not carried over: the spawn-per-device worker pool (`multi_process_evaluation`, evaluator.py:97-146) — `run` evaluates
-on `devices[0]`; datasets / visualisation helpers."""
+`multi_process_evaluation` / `worker` (evaluator.py:97-163): one spawned process per device, the dataset split in
+contiguous shreds, results returned through a queue; `run` uses it when more than one device is given. Not carried over:
+datasets / visualisation helpers."""
 import os
 import time
 
@@ -43,6 +44,8 @@ class Evaluator(object):
             ensure_dir(save_path)
         self.show_image = show_image
         self.crop_batch = crop_batch     # windows per batched forward
+        self.context = None              # torch.multiprocessing 'spawn' context, created on first use (evaluator.py:36-37)
+        self.results_queue = None
 
     # ------------------------------------------------------------------ driver (evaluator.py:43-95)
     def run(self, model_path, model_indice, log_file, log_file_link):
@@ -66,7 +69,7 @@ class Evaluator(object):
         for model in models:
             logger.info("Load Model: %s" % model)
             self.val_func = load_model(self.network, model)
-            result_line = self.single_process_evalutation()
+            result_line = (self.multi_process_evaluation() if len(self.devices) > 1 else self.single_process_evalutation())
             results.write('Model: ' + model + '\n')
             results.write(result_line)
             results.write('\n')
@@ -81,6 +84,51 @@ class Evaluator(object):
         result_line = self.compute_metric(all_results)
         logger.info('Evaluation Elapsed Time: %.2fs' % (time.perf_counter() - t0))
         return result_line
+
+    def multi_process_evaluation(self):
+        """evaluator.py:97-146: one process per device over contiguous shreds of the dataset, results through a queue"""
+        import torch.multiprocessing as mp
+        t0 = time.perf_counter()
+        if self.context is None:
+            self.context = mp.get_context('spawn')
+        self.results_queue = self.context.Queue(max(1, self.ndata))
+        nr_devices = len(self.devices)
+        stride = int(np.ceil(self.ndata / nr_devices))
+        shreds = [list(range(d * stride, min((d + 1) * stride, self.ndata))) for d in range(nr_devices)]
+        all_results = []
+        if nr_devices > 1:
+            procs = []
+            for d, device in enumerate(self.devices):
+                logger.info('GPU %s handle %d data.' % (device, len(shreds[d])))
+                procs.append(self.context.Process(target=self.worker, args=(shreds[d], device)))
+            for p in procs:
+                p.start()
+            for _ in range(self.ndata):
+                all_results.append(self.results_queue.get())
+                if self.verbose:
+                    self.compute_metric(all_results)
+            for p in procs:
+                p.join()
+        else:
+            self.worker(shreds[0], self.devices[0])
+            for _ in range(self.ndata):
+                all_results.append(self.results_queue.get())
+        result_line = self.compute_metric(all_results)
+        logger.info('Evaluation Elapsed Time: %.2fs' % (time.perf_counter() - t0))
+        return result_line
+
+    def worker(self, shred_list, device):
+        """evaluator.py:148-163"""
+        t0 = time.time()
+        logger.info('Load Model on Device %s: %.2fs' % (device, time.time() - t0))
+        for idx in shred_list:
+            results_dict = self.func_per_iteration(self.dataset[idx], device)
+            self.results_queue.put(results_dict)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['context'] = None          # a multiprocessing context is not picklable; the queue travels as a Process argument owner
+        return state
 
     def func_per_iteration(self, data, device):
         raise NotImplementedError

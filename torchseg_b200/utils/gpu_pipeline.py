@@ -27,7 +27,11 @@ def normalize_lut(mean, std):
 
 
 class TrainPreGPU(object):
-    def __init__(self, img_mean, img_std, crop_size, scale_array, device, bgr_input=True):
+    def __init__(self, img_mean, img_std, crop_size, scale_array, device, bgr_input=True, edge_labels=False):
+        """edge_labels=True: DFN's TrainPre (model/dfn/cityscapes.dfn.R101_v1c/dataloader.py:11-44) — __call__ returns a
+        third tensor 'aux_label' (Canny + 7x7 dilate border map ∈ {0, 1, 255}, tsb_edge_labels)"""
+        self.edge_labels = bool(edge_labels)
+        self._ws = None
         self.crop_h, self.crop_w = int(crop_size[0]), int(crop_size[1])
         self.scale_array = list(scale_array) if scale_array is not None else None
         self.device = torch.device(device)
@@ -72,4 +76,12 @@ class TrainPreGPU(object):
         label = torch.empty((n, self.crop_h, self.crop_w), dtype=torch.int64, device=self.device)
         ops.call("tsb_train_preprocess", ops.ptr(desc), n, self.crop_h, self.crop_w, int(self.bgr_input), ops.ptr(self.lut),
                  0.0, 255, ops.ptr(data), ops.ptr(label), ops.stream())
-        return data, label
+        if not self.edge_labels:
+            return data, label
+        need = int(ops._lib.lib().tsb_edge_labels_workspace_bytes(n, self.crop_h, self.crop_w))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        aux = torch.empty((n, self.crop_h, self.crop_w), dtype=torch.int64, device=self.device)
+        ops.call("tsb_edge_labels", ops.ptr(desc), n, self.crop_h, self.crop_w, 255, ops.ptr(self._ws), need, ops.ptr(aux),
+                 ops.stream())
+        return data, label, aux
