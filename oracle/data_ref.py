@@ -92,9 +92,11 @@ def _crop_pad(img, pos, crop_size, value):
     return out
 
 
-def train_pre(img_rgb, gt, params, crop_size, mean, std):
+def train_pre(img_rgb, gt, params, crop_size, mean, std, gt_down_sampling=1):
     """img_rgb: uint8 [H,W,3] (after BaseDataset's `img[:, :, ::-1]`, BaseDataset.py:45), gt: uint8 [H,W].
-    Returns (float32 [3,ch,cw], int64 [ch,cw]) exactly as BaseDataset.__getitem__ hands them to the loader (:49-51)."""
+    Returns (float32 [3,ch,cw], int64 [ch,cw]) exactly as BaseDataset.__getitem__ hands them to the loader (:49-51).
+    gt_down_sampling > 1: the speed config (model/bisenet/cityscapes.bisenet.R18.speed/dataloader.py:28-30) resizes the
+    cropped label to (cw // ds, ch // ds) with INTER_NEAREST."""
     if params["flip"]:
         img_rgb = img_rgb[:, ::-1]
         gt = gt[:, ::-1]
@@ -107,6 +109,8 @@ def train_pre(img_rgb, gt, params, crop_size, mean, std):
     pos = (params["pos_h"], params["pos_w"])
     p_img = _crop_pad(x, pos, crop_size, 0)
     p_gt = _crop_pad(gt, pos, crop_size, 255)
+    if gt_down_sampling > 1:
+        p_gt = resize_nearest(np.ascontiguousarray(p_gt), crop_size[1] // gt_down_sampling, crop_size[0] // gt_down_sampling)
     return np.ascontiguousarray(p_img.transpose(2, 0, 1)).astype(np.float32), np.ascontiguousarray(p_gt).astype(np.int64)
 
 

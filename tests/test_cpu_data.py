@@ -105,3 +105,14 @@ def test_train_pre_dfn_oracle_vs_live_reference_golden():
         data, label, aux = data_ref.train_pre_dfn(bgr[:, :, ::-1], gt, prm, crop, mean, std)
         assert _sha(data) == ent["data_sha256"] and _sha(label) == ent["label_sha256"], seed
         assert _sha(aux) == ent["aux_sha256"] and int((aux == 1).sum()) == ent["aux_ones"], seed
+
+
+def test_train_pre_speed_config_label_downsampling_vs_live_reference_golden():
+    from oracle import data_ref
+    bgr, gt, crop, scales, mean, std = pipeline_case()
+    for seed, ent in GOLD["cases_speed"].items():
+        random.seed(int(seed))
+        prm = data_ref.draw_params(bgr.shape[:2], crop, scales)
+        _, label = data_ref.train_pre(bgr[:, :, ::-1], gt, prm, crop, mean, std, gt_down_sampling=8)
+        assert list(label.shape) == ent["label_shape"] == [crop[0] // 8, crop[1] // 8]
+        assert _sha(label) == ent["label_sha256"], seed

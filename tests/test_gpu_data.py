@@ -117,3 +117,15 @@ def test_dfn_pipeline_cityscapes_frame_vs_oracle(cuda, seed):
     assert np.array_equal(label[0].cpu().numpy(), ref_l)
     assert np.array_equal(aux[0].cpu().numpy(), ref_a), (ref_prm, int((aux[0].cpu().numpy() != ref_a).sum()))
     assert np.array_equal(data[0].cpu().numpy().view(np.uint32), ref_d.view(np.uint32))
+
+
+def test_pipeline_speed_config_label_downsampling(cuda):
+    """cityscapes.bisenet.R18.speed: labels at 1/8 resolution (dataloader.py:28-30) vs the live-reference fixtures"""
+    from torchseg_b200.utils.gpu_pipeline import TrainPreGPU
+    bgr, gt, crop, scales, mean, std = pipeline_case()
+    pre = TrainPreGPU(mean, std, crop, scales, cuda, gt_down_sampling=8)
+    for seed, ent in GOLD["cases_speed"].items():
+        random.seed(int(seed))
+        data, label = pre([torch.from_numpy(bgr).to(cuda)], [torch.from_numpy(gt).to(cuda)])
+        assert list(label.shape[1:]) == ent["label_shape"] and _sha(label[0]) == ent["label_sha256"], seed
+        assert tuple(data.shape[2:]) == tuple(crop)

@@ -171,6 +171,18 @@ def main():
         b = torch.from_numpy(np.ascontiguousarray(p_gt)).long()
         pipe[str(seed)] = {"data_sha256": sha(a), "label_sha256": sha(b), "shape": list(a.shape),
                            "data_sum": float(a.double().sum()), "label_sum": int(b.sum())}
+    # speed config (cityscapes.bisenet.R18.speed/dataloader.py:11-36): the cropped label down-sampled x8 by INTER_NEAREST
+    bgr, gt, crop, scales, mean, std = pipeline_case()
+    dl = rl.load_train_pre('bisenet/cityscapes.bisenet.R18.speed', train_scale_array=scales, image_height=crop[0],
+                           image_width=crop[1], image_mean=mean, image_std=std, gt_down_sampling=8)
+    pre = dl.TrainPre(mean, std)
+    pipe_speed = {}
+    for seed in range(6):
+        random.seed(seed)
+        p_img, p_gt, _ = pre(bgr[:, :, ::-1], gt)
+        b = torch.from_numpy(np.ascontiguousarray(p_gt)).long()
+        pipe_speed[str(seed)] = {"label_sha256": sha(b), "label_shape": list(b.shape)}
+
     # DFN TrainPre (dfn dataloader.py:11-44): same pipeline + the Canny / dilate border label, its own scale array
     from golden_cases import pipeline_case_dfn
     bgr, gt, crop, scales, mean, std = pipeline_case_dfn()
@@ -187,7 +199,7 @@ def main():
         pipe_dfn[str(seed)] = {"data_sha256": sha(a), "label_sha256": sha(b), "aux_sha256": sha(c), "shape": list(a.shape),
                                "aux_ones": int((c == 1).sum()), "aux_pad": int((c == 255).sum())}
     with open(os.path.join(OUT, "data_pipeline.json"), "w") as f:
-        json.dump({"cv2": __import__("cv2").__version__, "cases": pipe, "cases_dfn": pipe_dfn}, f, indent=1, sort_keys=True)
+        json.dump({"cv2": __import__("cv2").__version__, "cases": pipe, "cases_dfn": pipe_dfn, "cases_speed": pipe_speed}, f, indent=1, sort_keys=True)
 
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "reference_outputs.json"), "w") as f:

@@ -27,10 +27,14 @@ def normalize_lut(mean, std):
 
 
 class TrainPreGPU(object):
-    def __init__(self, img_mean, img_std, crop_size, scale_array, device, bgr_input=True, edge_labels=False):
+    def __init__(self, img_mean, img_std, crop_size, scale_array, device, bgr_input=True, edge_labels=False,
+                 gt_down_sampling=1):
         """edge_labels=True: DFN's TrainPre (model/dfn/cityscapes.dfn.R101_v1c/dataloader.py:11-44) — __call__ returns a
         third tensor 'aux_label' (Canny + 7x7 dilate border map ∈ {0, 1, 255}, tsb_edge_labels)"""
         self.edge_labels = bool(edge_labels)
+        # speed config (cityscapes.bisenet.R18.speed/dataloader.py:28-30, config.py:66): the cropped label is resized to
+        # (cw // ds, ch // ds) with INTER_NEAREST = index floor(d · ds) — every ds-th pixel, a strided view
+        self.gt_down_sampling = int(gt_down_sampling)
         self._ws = None
         self.crop_h, self.crop_w = int(crop_size[0]), int(crop_size[1])
         self.scale_array = list(scale_array) if scale_array is not None else None
@@ -76,6 +80,9 @@ class TrainPreGPU(object):
         label = torch.empty((n, self.crop_h, self.crop_w), dtype=torch.int64, device=self.device)
         ops.call("tsb_train_preprocess", ops.ptr(desc), n, self.crop_h, self.crop_w, int(self.bgr_input), ops.ptr(self.lut),
                  0.0, 255, ops.ptr(data), ops.ptr(label), ops.stream())
+        ds = self.gt_down_sampling
+        if ds > 1:
+            label = label[:, ::ds, ::ds][:, :self.crop_h // ds, :self.crop_w // ds].contiguous()
         if not self.edge_labels:
             return data, label
         need = int(ops._lib.lib().tsb_edge_labels_workspace_bytes(n, self.crop_h, self.crop_w))
