@@ -366,6 +366,34 @@ maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restr
 template <typename A, typename B> struct SameT { static constexpr bool v = false; };
 template <typename A> struct SameT<A, A> { static constexpr bool v = true; };
 
+
+// S = 1 (global average pool: ARM / FFM / global-context squeezes, seg_oprs.py:200,223, bisenet network.py:35): the backward is
+// a broadcast of dout[n, c] / (H·W) over the map. The generic kernel spends ~10 integer divisions per 16-byte vector on the bin
+// search (ncu: 437 GB/s for a pure 71 MB write); this one is a plain vector store walk.
+__global__ void __launch_bounds__(kThreads)
+global_avgpool_bwd_kernel(const float* __restrict__ dout, int C8, long long hw, long long total, float inv_area,
+                          __nv_bfloat16* __restrict__ din, int ics, int accumulate) {
+    const long long stride_ = (long long)gridDim.x * kThreads;
+    VecWalk wk_(C8, (long long)blockIdx.x * kThreads + threadIdx.x, stride_);
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += stride_, wk_.next()) {
+        const int c8 = wk_.c8;
+        const long long pix = wk_.p;
+        const long long n = pix / hw;
+        float g[8];
+        ldg8f(dout + (n * C8 + c8) * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] *= inv_area;
+        __nv_bfloat16* dst = din + pix * ics + c8 * 8;
+        if (accumulate) {
+            float old[8];
+            Vec8<__nv_bfloat16>::load(dst, old);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] += old[k];
+        }
+        Vec8<__nv_bfloat16>::store(dst, g);
+    }
+}
+
 }  // namespace
 
 #define TSB_DT_OK(dt) ((dt) == TSB_F32 || (dt) == TSB_BF16)
@@ -460,6 +488,12 @@ extern "C" int tsb_adaptive_avgpool_bwd(const float* dout, int N, int C, int H, 
     TSB_REQUIRE(C % 8 == 0 && ics % 8 == 0 && tsb_aligned16(din) && tsb_aligned16(dout), "tsb_adaptive_avgpool_bwd: C, ics multiples of 8");
     long long total = (long long)N * H * W * (C / 8);
     int grid = tsb_grid_for(total, kThreads, 8);
+    if (S == 1) {
+        global_avgpool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(dout, C / 8, (long long)H * W, total, 1.0f / (float)(H * W),
+                                                                               (__nv_bfloat16*)din, ics, accumulate);
+        TSB_CUDA_CHECK_LAUNCH("global_avgpool_bwd");
+        return TSB_OK;
+    }
     adaptive_avgpool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(dout, N, C / 8, H, W, S, (__nv_bfloat16*)din, ics, accumulate);
     TSB_CUDA_CHECK_LAUNCH("adaptive_avgpool_bwd");
     return TSB_OK;

@@ -233,8 +233,6 @@ class _PeerExchange(object):
         # the exchange counter lives on the device (pre-incremented by every exchange kernel): identical on all ranks
         # because all ranks issue the same exchanges, and replayable inside a captured CUDA graph
         self.seq_dev = torch.zeros(1, dtype=torch.int32, device=device)
-        torch.cuda.synchronize(device)
-        dist.barrier(group=pg)      # every rank's buffer is zeroed before anybody's first exchange can write into it
 
     def allreduce(self, buf, acc_hi=None, acc_lo=None):
         call("tsb_p2p_allreduce_sum", ptr(buf), buf.numel(), ctypes.cast(self.peers, ctypes.c_void_p), self.rank, self.world,
@@ -242,20 +240,34 @@ class _PeerExchange(object):
 
 
 def _peer_exchange(device):
-    """the NVLink exchange object, or None (single process, CPU / gloo, TSB_SYNCBN_P2P=0, no symmetric memory)"""
+    """the NVLink exchange object, or None (single process, CPU / gloo, TSB_SYNCBN_P2P=0, no symmetric memory).
+    Collective: every rank of the SyncBN group reaches this at the same point (its first exchange), and the ranks AGREE on
+    the outcome — a rank that could not set the exchange up while its peers spin in the kernel would deadlock the job."""
     if _sync["world"] <= 1 or device.type != "cuda":
         return None
     if not _sync["p2p_tried"]:
         _sync["p2p_tried"] = True
         import os
+        import sys
+        import torch.distributed as dist
+        x, why = None, "disabled by TSB_SYNCBN_P2P=0"
         if os.environ.get("TSB_SYNCBN_P2P", "1") != "0":
             try:
-                _sync["p2p"] = _PeerExchange(_sync["group"], _sync["world"], device)
+                x = _PeerExchange(_sync["group"], _sync["world"], device)
             except Exception as e:  # noqa: BLE001 — no NVLink P2P / symmetric memory on this box: keep NCCL
-                import sys
-                sys.stderr.write("torchseg_b200: NVLink SyncBN exchange unavailable (%s: %s); using NCCL all-reduce\n" % (
-                    type(e).__name__, str(e).split("\n")[0][:200]))
-                _sync["p2p"] = None
+                x, why = None, "%s: %s" % (type(e).__name__, str(e).split("\n")[0][:200])
+        ok = torch.tensor([1.0 if x is not None else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=_sync["group"])
+        if float(ok.item()) < 1.0:
+            if x is not None:
+                why = "another rank could not set it up"
+            x = None
+            if os.environ.get("TSB_SYNCBN_P2P", "1") != "0":
+                sys.stderr.write("torchseg_b200: NVLink SyncBN exchange unavailable (%s); using NCCL all-reduce\n" % why)
+        else:
+            torch.cuda.synchronize(device)
+            dist.barrier(group=_sync["group"])   # every rank's buffer is zeroed before anybody's first exchange writes into it
+        _sync["p2p"] = x
     return _sync["p2p"]
 
 
