@@ -341,6 +341,76 @@ def run_eval_bench(args, device):
     print(json.dumps(line))
 
 
+def run_pipeline_bench(args, device):
+    """the device input pipeline (tsb_train_preprocess / tsb_edge_labels behind TrainPreGPU) on a batch of
+    decoded Cityscapes-size frames, against the cv2 sequence the reference's TrainPre runs per sample on one host core
+    (dataloader.py:16-33; the reference uses 24 worker processes). Secondary line (profiles/)."""
+    import random
+    import numpy as np
+    from torchseg_b200.utils.gpu_pipeline import TrainPreGPU
+    n = BATCH_PER_GPU
+    mean, std = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+    rng = np.random.default_rng(0)
+    frames = [rng.integers(0, 256, (1024, 2048, 3), dtype=np.uint8) for _ in range(n)]
+    gts = [rng.integers(0, 19, (1024, 2048), dtype=np.uint8) for _ in range(n)]
+    for g in gts:
+        for _ in range(40):
+            y0, x0 = rng.integers(0, 1000), rng.integers(0, 2000)
+            g[y0:y0 + rng.integers(20, 300), x0:x0 + rng.integers(20, 500)] = rng.integers(0, 19)
+    fd = [torch.from_numpy(f).to(device) for f in frames]
+    gd = [torch.from_numpy(g).to(device) for g in gts]
+    out = {}
+    peaks = load_peaks()
+    for name, crop, scales, edge in (("bisenet_1024", (1024, 1024), [0.75, 1, 1.25, 1.5, 1.75, 2.0], False),
+                                     ("dfn_800_edge_labels", (800, 800), [0.5, 0.75, 1, 1.5, 1.75, 2.0], True)):
+        pre = TrainPreGPU(mean, std, crop, scales, device, bgr_input=True, edge_labels=edge)
+        random.seed(1)
+        params = [pre.draw((1024, 2048)) for _ in range(n)]
+        for _ in range(3):
+            res = pre(fd, gd, params)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            res = pre(fd, gd, params)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out_bytes = sum(t.numel() * t.element_size() for t in res)
+        # algorithmic bytes: every output element written once + the source pixels of the crop window read once
+        src_bytes = sum(min(p["sh"], crop[0]) * min(p["sw"], crop[1]) / ((p["sh"] / 1024.0) * (p["sw"] / 2048.0)) * 4 for p in params)
+        entry = dict(value=n / (ms / 1000.0), unit="images/sec", ms_per_batch=ms, batch=n,
+                     algorithmic_gb_per_s=(out_bytes + src_bytes) / ms / 1e6, hbm_peak_gb_per_s=peaks["hbm_gbs"])
+        # the cv2 sequence of the reference TrainPre on one host core, same parameters (2 samples)
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            k7 = cv2.getStructuringElement(cv2.MORPH_RECT, (7, 7))
+            t0 = time.perf_counter()
+            for i in range(2):
+                p, img, gt = params[i], frames[i][:, :, ::-1], gts[i]
+                if p["flip"]:
+                    img, gt = cv2.flip(img, 1), cv2.flip(gt, 1)
+                img = cv2.resize(img, (p["sw"], p["sh"]), interpolation=cv2.INTER_LINEAR)
+                gt = cv2.resize(gt, (p["sw"], p["sh"]), interpolation=cv2.INTER_NEAREST)
+                if edge:
+                    g0 = gt.copy()
+                    g0[gt == 255] = 0
+                    cgt = cv2.dilate(cv2.Canny(g0, 5, 5, apertureSize=7), k7)
+                x = ((img.astype(np.float32) / 255.0) - mean) / std
+                x = x[p["pos_h"]:p["pos_h"] + crop[0], p["pos_w"]:p["pos_w"] + crop[1]]
+                x = np.ascontiguousarray(x.transpose(2, 0, 1)).astype(np.float32)
+            entry["cv2_one_core_images_per_sec"] = 2 / (time.perf_counter() - t0)
+        except ImportError:
+            pass
+        out[name] = entry
+    line = {"metric": "images/sec training input pipeline (1024x2048 uint8 frames -> fp32 NCHW crop + int64 labels)",
+            "value": out["bisenet_1024"]["value"], "unit": "images/sec", "n_gpus": 1, "steps": args.steps, "dtype": "u8",
+            "data": "synthetic", "config": {"workload": "TrainPre on the device: mirror, cv2-exact scale, normalize, crop/pad (+ DFN border labels)",
+                                            "batch": n}, "detail": out}
+    print(json.dumps(line))
+
+
 def pick_threads():
     """torch CPU ops do not scale to every hardware thread of a big host: calibrate on a tiny step and use the
     fastest of {all, 64, 32, 16} threads (reported as `cores`)."""
@@ -393,6 +463,7 @@ def main():
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="single GPU: time eager launches only (default: the step is ONE CUDA graph replay, "
                          "engine.graph.GraphedTrainStep; the eager time is reported beside it)")
+    ap.add_argument("--pipeline", action="store_true", help="secondary line: device input pipeline throughput, 1 GPU")
     ap.add_argument("--eval", action="store_true", help="secondary line: evaluator forward throughput (BN folding), 1 GPU")
     ap.add_argument("--default-stream", action="store_true",
                     help="run on the legacy default stream (default: a non-blocking side stream, which whole-step graph capture needs)")
@@ -411,6 +482,8 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", init_method="env://", device_id=device)
+    if args.pipeline:
+        return run_pipeline_bench(args, device)
     if args.eval:
         if args.batch == BATCH_PER_GPU:
             args.batch = 4
