@@ -291,6 +291,20 @@ int tsb_pack_wt_multi(const void* wb_flat_bf16, void* wt_flat_bf16, const void* 
                       int ntensors, int nblocks, tsb_stream_t stream);
 
 /* ================================================================================================
+ * Fused bilinear up-sampling (align_corners=True, to H x W) + cross-entropy(mean over valid pixels, ignore index) for many
+ * classes (1 <= C <= 152) — replaces F.interpolate → log_softmax → nn.CrossEntropyLoss of the PSPNet / PSANet heads
+ * (model/pspnet/ade.pspnet.R101_v1c/network.py:46-57, model/psanet/.../network.py:46-55); the [N,C,H,W] logits are never written.
+ * logits_lo: fp32 NHWC [N,h,w,cs]; lse: fp32 [N*H*W] (log-sum-exp per pixel, kept for the backward); state: 8 words
+ * (zeroed inside): {double Σ loss, valid count, loss, 1/count}. backward: dlogits_lo (fp32 NHWC, caller-zeroed) +=
+ * d loss / d logits_lo · *gscale.
+ * ============================================================================================== */
+int tsb_ce_up_fwd(const float* logits_lo, int cs, int h, int w, const int64_t* labels, int N, int C, int H, int W,
+                  int ignore_label, float* lse, uint32_t* state, float* loss_out, tsb_stream_t stream);
+int tsb_ce_up_bwd(const float* logits_lo, int cs, int h, int w, const int64_t* labels, const float* lse, int N, int C,
+                  int H, int W, int ignore_label, const uint32_t* state, const float* gscale, float* dlogits_lo,
+                  tsb_stream_t stream);
+
+/* ================================================================================================
  * Sigmoid focal loss (DFN border branch) — SigmoidFocalLoss.forward loss_opr.py:23-45, reproduced
  * as is (incl. the sigmoid-inside-logsumexp quirk). pred fp32/bf16 [n], target int64.
  * ============================================================================================== */

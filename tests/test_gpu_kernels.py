@@ -403,3 +403,40 @@ def test_ohem_exact_kernels_match_generic_at_full_size(cuda):
     assert s1["T"] == s0["T"] and s1["kept"] == s0["kept"] and s1["active"] == s0["active"]
     assert abs(l1 - l0) <= 1e-6 * abs(l0)
     assert rel_err(g1, g0) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [(150, 12, 20, 96, 160, -1), (150, 11, 13, 83, 99, -1), (21, 9, 9, 72, 72, 255), (37, 6, 70, 48, 560, 255)],
+                         ids=["ade150_x8", "ade150_odd_size", "c21_x8", "c37_wide"])
+def test_ce_up_fused_matches_torch(cuda, cfg):
+    """fused bilinear up-sampling + cross-entropy for many classes (tsb_ce_up_*, the PSPNet / PSANet head tail): loss and
+    d loss / d low-res logits against F.interpolate(size=, align_corners=True) + F.cross_entropy in fp32 on the GPU;
+    x8 and non-integer scale (the 713 / 473 crops), ignored pixels, strips wider than one CTA"""
+    ops = _ops()
+    C, h, w, H, W, ign = cfg
+    N = 3
+    g = torch.Generator().manual_seed(C + h + W)
+    lo = torch.randn(N, C, h, w, generator=g) * 2
+    labels = torch.randint(0, C, (N, H, W), generator=g)
+    labels[:, : max(1, H // 10)] = ign
+    labels[torch.rand(N, H, W, generator=g) < 0.05] = ign
+    cs = (C + 31) // 32 * 32
+    lo_d = ops.nhwc_zeros(N, C, h, w, dtype=torch.float32, device=cuda, cs=cs)
+    lo_d.copy_(lo.to(cuda))
+    lo_d.requires_grad_(True)
+    loss = ops.CEUpFn.apply(lo_d, labels.to(cuda), H, W, C, ign)
+    (loss * 1.7).backward()
+    lo_t = lo.to(cuda).clone().requires_grad_(True)
+    ref = F.cross_entropy(F.interpolate(lo_t, size=(H, W), mode="bilinear", align_corners=True), labels.to(cuda), ignore_index=ign)
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) < 2e-5 * abs(ref.item()), (loss.item(), ref.item())
+    assert rel_err(lo_d.grad, lo_t.grad) < 2e-4, rel_err(lo_d.grad, lo_t.grad)
+    # channels beyond C in the padded NHWC gradient buffer stay untouched
+    assert tuple(lo_d.grad.shape) == (N, C, h, w)
+
+
+def test_ce_up_all_ignored_is_nan_like_torch(cuda):
+    ops = _ops()
+    lo = ops.nhwc_zeros(1, 150, 4, 4, dtype=torch.float32, device=cuda, cs=160)
+    labels = torch.full((1, 32, 32), -1, dtype=torch.int64, device=cuda)
+    loss = ops.CEUpFn.apply(lo, labels, 32, 32, 150, -1)
+    assert loss.item() != loss.item()        # NaN: mean over zero valid pixels, like nn.CrossEntropyLoss

@@ -74,6 +74,8 @@ _SIGS = {
     "tsb_sgd_flat_pack": [P, P, P, L, P, P, P, I, F, F, I, P, P],
     "tsb_pack_wt_multi": [P, P, P, P, I, I, P],
     "tsb_sigmoid_focal_fwd_bwd": [P, I, P, L, I, F, F, P, P, P],
+    "tsb_ce_up_fwd": [P, I, I, I, P, I, I, I, I, I, P, P, P, P],
+    "tsb_ce_up_bwd": [P, I, I, I, P, P, I, I, I, I, I, P, P, P, P],
     "tsb_train_preprocess": [P, I, I, I, I, P, F, I, P, P, P],
     "tsb_edge_labels": [P, I, I, I, I, P, c_size_t, P, P],
     "tsb_p2p_allreduce_sum": [P, I, P, I, I, c_uint, P, I, I, P, P, P],

@@ -16,7 +16,7 @@ from .. import ops
 from ..base_model import resnet50, resnet101
 from ..seg_opr.seg_oprs import ConvBnRelu, conv_plain, _as_act
 from .bisenet import _UpsampleLogitsFn
-from .pspnet import _ignore_index_of, _dropout2d, _config, PSPNet as _PSPNetBase
+from .pspnet import _ignore_index_of, _dropout2d, _config, head_loss, PSPNet as _PSPNetBase
 
 
 class PSANet(nn.Module):
@@ -48,13 +48,12 @@ class PSANet(nn.Module):
         # network.py:46-49 upsample by scale_factor=8, which only reproduces the input size when it is a multiple of 8
         # (480); `size=` semantics — identical numbers for those sizes — also admit the 713 / 473 crops of BASELINE.json
         H, W = int(data.shape[2]), int(data.shape[3])
-        psa_fm = _UpsampleLogitsFn.apply(self.psa_layer(blocks[-1]), H, W)      # network.py:46-47
+        psa_lo = self.psa_layer(blocks[-1])
         if label is None:
-            return torch.log_softmax(psa_fm, dim=1)
-        aux_fm = _UpsampleLogitsFn.apply(self._aux_logits(blocks[-2]), H, W)
+            return torch.log_softmax(_UpsampleLogitsFn.apply(psa_lo, H, W), dim=1)   # network.py:46-51
         ign = _ignore_index_of(self.criterion)
-        loss = ops.OhemCEFn.apply(psa_fm, label, ign, 1.0, 0, None)
-        aux_loss = ops.OhemCEFn.apply(aux_fm, label, ign, 1.0, 0, None)
+        loss = head_loss(psa_lo, label, H, W, self.out_planes, ign)
+        aux_loss = head_loss(self._aux_logits(blocks[-2]), label, H, W, self.out_planes, ign)
         return loss + self.aux_loss_ratio * aux_loss                         # network.py:55
 
 

@@ -2,9 +2,9 @@
 (/root/reference/model/pspnet/ade.pspnet.R101_v1c/network.py:14-109) on the libtsb path.
 
 Training forward returns `loss + 0.4 * aux_loss` (network.py:53-57). The reference applies log_softmax and then
-nn.CrossEntropyLoss (a second, idempotent log_softmax); here the ×8 bilinear up-sampling writes NCHW fp32 logits and
-the cross-entropy (ignore_index taken from the criterion) runs through the OHEM kernels with min_kept = 0, which is
-exactly CrossEntropyLoss(mean, ignore_index)."""
+nn.CrossEntropyLoss (a second, idempotent log_softmax); here each head ends in ONE fused kernel pair (bilinear up-sampling to
+the input size + cross-entropy with the criterion's ignore_index, `ops.CEUpFn`): the 150-class full-resolution logits are
+never materialised. (`FUSED_CE = False` restores the materialised form: NCHW fp32 logits + the OHEM kernels with min_kept = 0.)"""
 from collections import OrderedDict
 from functools import partial
 
@@ -30,6 +30,18 @@ except Exception:  # noqa: BLE001
 
 def _ignore_index_of(criterion, default=-1):
     return int(getattr(criterion, "ignore_index", getattr(criterion, "ignore_label", default)))
+
+
+FUSED_CE = True   # training heads: fused bilinear up-sampling + cross-entropy (tsb_ce_up_*); False = materialised logits
+
+
+def head_loss(lo, label, H, W, num_classes, ignore_index):
+    """bilinear(align_corners) up-sampling of the low-resolution fp32 logits to H x W + CrossEntropyLoss(mean, ignore_index)
+    (network.py:46-55). Fused: the [N, C, H, W] logits are never written (C <= 152); otherwise the up-sampled NCHW fp32
+    logits go through the OHEM kernels with min_kept = 0, which is exactly CrossEntropyLoss."""
+    if FUSED_CE and num_classes <= ops.FUSED_CE_MAX_CLASSES:
+        return ops.CEUpFn.apply(lo, label, H, W, num_classes, ignore_index)
+    return ops.OhemCEFn.apply(_UpsampleLogitsFn.apply(lo, H, W), label, ignore_index, 1.0, 0, None)
 
 
 def _dropout2d(x, p, training):
@@ -74,13 +86,11 @@ class PSPNet(nn.Module):
         # (480); `size=` semantics — identical numbers for those sizes — also admit the 713 / 473 crops of BASELINE.json
         H, W = int(data.shape[2]), int(data.shape[3])
         psp_lo = self.psp_layer(blocks[-1])
-        psp_fm = _UpsampleLogitsFn.apply(psp_lo, H, W)            # network.py:46-47
         if label is None:
-            return torch.log_softmax(psp_fm, dim=1)
-        aux_fm = _UpsampleLogitsFn.apply(self._aux_logits(blocks[-2]), H, W)
+            return torch.log_softmax(_UpsampleLogitsFn.apply(psp_lo, H, W), dim=1)   # network.py:46-51
         ign = _ignore_index_of(self.criterion)
-        loss = ops.OhemCEFn.apply(psp_fm, label, ign, 1.0, 0, None)
-        aux_loss = ops.OhemCEFn.apply(aux_fm, label, ign, 1.0, 0, None)
+        loss = head_loss(psp_lo, label, H, W, self.out_planes, ign)
+        aux_loss = head_loss(self._aux_logits(blocks[-2]), label, H, W, self.out_planes, ign)
         return loss + self.aux_loss_ratio * aux_loss           # network.py:56
 
     def _nostride_dilate(self, m, dilate):

@@ -1054,6 +1054,43 @@ class OhemUpCEFn(torch.autograd.Function):
         return d, None, None, None, None, None, None, None, None
 
 
+class CEUpFn(torch.autograd.Function):
+    """Fused head tail for MANY classes (ADE's 150): bilinear up-sampling (align_corners) of the LOW-res fp32 NHWC logits to
+    H x W + CrossEntropyLoss(mean, ignore_index); the full-resolution [N,C,H,W] logits are never written
+    (pspnet network.py:46-57, psanet network.py:46-55). 1 <= C <= 152."""
+
+    @staticmethod
+    def forward(ctx, lo, target, H, W, num_classes, ignore_label):
+        N, _, h, w = lo.shape
+        assert lo.dtype == torch.float32
+        target = target.contiguous()
+        cs = cs_of(lo)
+        dev = lo.device
+        state = torch.empty((8,), dtype=torch.int32, device=dev)
+        lse = torch.empty((N * H * W,), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        call("tsb_ce_up_fwd", ptr(lo), cs, h, w, ptr(target), N, int(num_classes), int(H), int(W), int(ignore_label), ptr(lse),
+             ptr(state), ptr(loss), stream())
+        ctx.save_for_backward(lo, target, lse, state)
+        ctx.cfg = (int(H), int(W), int(num_classes), int(ignore_label))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lo, target, lse, state = ctx.saved_tensors
+        H, W, C, ignore_label = ctx.cfg
+        N, Cl, h, w = lo.shape
+        cs = cs_of(lo)
+        d = nhwc_zeros(N, Cl, h, w, dtype=torch.float32, device=lo.device, cs=cs)
+        g = g.to(torch.float32).contiguous()
+        call("tsb_ce_up_bwd", ptr(lo), cs, h, w, ptr(target), ptr(lse), N, C, H, W, ignore_label, ptr(state), ptr(g), ptr(d),
+             stream())
+        return d, None, None, None, None, None
+
+
+FUSED_CE_MAX_CLASSES = 152   # tsb_ce_up_* register budget (38 class quads)
+
+
 def ohem_state_dict(state):
     """decode the OHEM state words (host sync) — for tests / logging"""
     s = state.cpu()
