@@ -90,7 +90,7 @@ ce_up_fwd_kernel(const float* __restrict__ lo, int cs, int h, int w, const int64
             if (4 * j + qd < C) ssum += __expf(v[j] - m);
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
-        const float lse = m + __logf(ssum);
+        const float lse = m + logf(ssum);
         const bool valid = xin && lab != (long long)ignore_label;
         if (qd == 0 && xin) {
             lse_out[((long long)n * H + y) * W + x] = lse;
