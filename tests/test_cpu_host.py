@@ -164,6 +164,19 @@ def _worker(rank, world, port, q):
                 # gradients are views into ONE flat buffer
                 lo = ddp.flat_grad.data_ptr()
                 assert lo <= p.grad.data_ptr() < lo + ddp.flat_grad.numel() * 4
+            # overlap=False (the form GraphedTrainStep captures): hooks reduce nothing, finish_reduce() issues ONE
+            # all-reduce of the whole flat buffer and averages it
+            ddp.overlap = False
+            ddp.zero_grad()
+            loss = sum(((rank + 2.0) * p).sum() for p in net.parameters())
+            loss.backward()
+            for p in net.parameters():                                                # still the local gradient
+                assert torch.allclose(p.grad, torch.full_like(p.grad, rank + 2.0))
+            ddp.finish_reduce()
+            expect = sum(range(2, world + 2)) / world
+            for p in net.parameters():
+                assert torch.allclose(p.grad, torch.full_like(p.grad, expect)), (rank, p.grad.flatten()[:3])
+            assert not ddp._pending
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         import traceback
